@@ -1,0 +1,393 @@
+// K3 (exact mode) - DRUNet convolutions as FP32 CUDA-core implicit GEMMs.
+//
+// Reference being replaced: the layers of UNetRes
+//   PyTorch_Denoiser/zhang_dpir_testing_code/network_unet.py:68-117, basicblock.py:61-98 (conv),
+//   :211-223 (ResBlock), :413-419 (ConvTranspose2d 2x2 s2), :437-443 (Conv2d 2x2 s2)
+// evaluated by denoiseImage_PnP_ADMM.m:88.  All layers are bias-free.
+//
+// Activations live in HBM as [S][Y][X][Ch] fp32 (channels innermost), X being the fastest
+// spatial index of whatever plane layout the caller uses; the weight packer (unetres.cu)
+// transposes the taps when the planes are MATLAB-ordered.  ReLU, the ResBlock residual and the
+// U-skip adds are fused into the producing conv's epilogue; the per-slice 0-1 normalisation
+// of PnP_ADMM.m:121 / :138 is folded into the head load and the tail store.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "conv_kernels.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// 3x3, stride 1, pad 1, Cin % 8 == 0, Cout % 64 == 0.  CTA: 8 x 16 output pixels x 64 couts.
+// ---------------------------------------------------------------------------------------
+constexpr int C3_KC = 8;
+constexpr int C3_PW = 20;  // patch row stride (18 used), keeps rows 16-byte aligned
+
+__global__ void __launch_bounds__(256) conv3x3_fp32_kernel(ConvParams p) {
+    __shared__ __align__(16) float patch[C3_KC][10][C3_PW];
+    __shared__ __align__(16) float wts[9][C3_KC][64];
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.W + 15) / 16;
+    const int ty0 = (blockIdx.x / tiles_x) * 8, tx0 = (blockIdx.x % tiles_x) * 16;
+    const int co0 = blockIdx.y * 64;
+    const int s = blockIdx.z;
+    const int pg = tid >> 4, cgp = tid & 15;
+    const int row = pg >> 1, xh = (pg & 1) * 8;
+    const float* in = p.in + (size_t)s * p.H * p.W * p.Cin;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int ci0 = 0; ci0 < p.Cin; ci0 += C3_KC) {
+        __syncthreads();
+        // input patch (10 x 18 pixels x 8 channels), zero padded
+        for (int t = tid; t < 360; t += 256) {
+            int pix = t % 180, half = t / 180;
+            int py = pix / 18, px = pix % 18;
+            int y = ty0 + py - 1, x = tx0 + px - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < p.H && x >= 0 && x < p.W)
+                v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)y * p.W + x) * p.Cin + ci0 + 4 * half));
+            patch[4 * half + 0][py][px] = v.x;
+            patch[4 * half + 1][py][px] = v.y;
+            patch[4 * half + 2][py][px] = v.z;
+            patch[4 * half + 3][py][px] = v.w;
+        }
+        // weights [tap][ci0..ci0+8][co0..co0+64]
+        for (int t = tid; t < 9 * C3_KC * 16; t += 256) {
+            int tap = t / (C3_KC * 16), r = t % (C3_KC * 16);
+            int k = r / 16, q = r % 16;
+            float4 v = __ldg(reinterpret_cast<const float4*>(p.w + ((size_t)tap * p.Cin + ci0 + k) * p.Cout + co0 + 4 * q));
+            *reinterpret_cast<float4*>(&wts[tap][k][4 * q]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ry = 0; ry < 3; ++ry) {
+#pragma unroll
+            for (int k = 0; k < C3_KC; ++k) {
+                float a[12];
+                const float* pr = &patch[k][row + ry][xh];
+                *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(pr);
+                *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(pr + 4);
+                *reinterpret_cast<float2*>(a + 8) = *reinterpret_cast<const float2*>(pr + 8);
+#pragma unroll
+                for (int sx = 0; sx < 3; ++sx) {
+                    float4 b = *reinterpret_cast<const float4*>(&wts[ry * 3 + sx][k][4 * cgp]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        acc[i][0] = fmaf(a[i + sx], b.x, acc[i][0]);
+                        acc[i][1] = fmaf(a[i + sx], b.y, acc[i][1]);
+                        acc[i][2] = fmaf(a[i + sx], b.z, acc[i][2]);
+                        acc[i][3] = fmaf(a[i + sx], b.w, acc[i][3]);
+                    }
+                }
+            }
+        }
+    }
+    const int y = ty0 + row;
+    if (y < p.H) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int x = tx0 + xh + i;
+            if (x >= p.W) continue;
+            size_t o = (((size_t)s * p.H + y) * p.W + x) * p.Cout + co0 + 4 * cgp;
+            float4 r = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (p.res1) {
+                float4 t = *reinterpret_cast<const float4*>(p.res1 + o);  // may alias out (in-place ResBlock)
+                r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+            }
+            if (p.res2) {
+                float4 t = *reinterpret_cast<const float4*>(p.res2 + o);
+                r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+            }
+            if (p.relu) {
+                r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(p.out + o) = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// 2x2 stride-2 conv (mode 0) and 2x2 stride-2 transposed conv (mode 1) as per-pixel GEMMs.
+//   down: M = S*Ho*Wo, K = 4*Cin (tap-major), N = Cout
+//   up:   M = S*Hi*Wi, K = Cin,               N = 4*Cout (tap-major), scattered to (2y+a, 2x+b)
+// 64 x 64 tile, 256 threads, 4 x 4 per thread, K chunks of 16.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resample_gemm_fp32_kernel(ConvParams p) {
+    __shared__ __align__(16) float As[16][64 + 4];
+    __shared__ __align__(16) float Bs[16][64];
+    const int tid = threadIdx.x;
+    const int up = p.mode;
+    const int Hi = p.H, Wi = p.W;  // input spatial size
+    const int Ho = up ? 2 * Hi : Hi / 2, Wo = up ? 2 * Wi : Wi / 2;
+    const int Hm = up ? Hi : Ho, Wm = up ? Wi : Wo;  // spatial size the GEMM rows enumerate
+    const int64_t Mtot = (int64_t)p.S * Hm * Wm;
+    const int K = up ? p.Cin : 4 * p.Cin;
+    const int N = up ? 4 * p.Cout : p.Cout;
+    const int64_t m0 = (int64_t)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    const int tm = tid >> 4, tn = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    // A loader: thread -> (row = tid / 4, 4 consecutive k = (tid % 4) * 4)
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    const int64_t lm = m0 + lr;
+    int ls = 0, ly = 0, lx = 0;
+    if (lm < Mtot) {
+        ls = (int)(lm / ((int64_t)Hm * Wm));
+        int rem = (int)(lm % ((int64_t)Hm * Wm));
+        ly = rem / Wm;
+        lx = rem % Wm;
+    }
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        __syncthreads();
+        {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lm < Mtot) {
+                int k = k0 + lk;
+                const float* src;
+                if (up) {
+                    src = p.in + (((size_t)ls * Hi + ly) * Wi + lx) * p.Cin + k;
+                } else {
+                    int tap = k / p.Cin, ci = k % p.Cin;
+                    src = p.in + (((size_t)ls * Hi + 2 * ly + (tap >> 1)) * Wi + 2 * lx + (tap & 1)) * p.Cin + ci;
+                }
+                v = __ldg(reinterpret_cast<const float4*>(src));
+            }
+            As[lk + 0][lr] = v.x;
+            As[lk + 1][lr] = v.y;
+            As[lk + 2][lr] = v.z;
+            As[lk + 3][lr] = v.w;
+            // B: 16 x 64 floats = 256 float4
+            int bk = tid >> 4, bq = tid & 15;
+            float4 w = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)(k0 + bk) * N + n0 + 4 * bq));
+            *reinterpret_cast<float4*>(&Bs[bk][4 * bq]) = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float4 a = *reinterpret_cast<const float4*>(&As[k][4 * tm]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[k][4 * tn]);
+            float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+                acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+                acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+                acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t m = m0 + 4 * tm + i;
+        if (m >= Mtot) continue;
+        int s = (int)(m / ((int64_t)Hm * Wm));
+        int rem = (int)(m % ((int64_t)Hm * Wm));
+        int y = rem / Wm, x = rem % Wm;
+        int n = n0 + 4 * tn;
+        size_t o;
+        if (up) {
+            int tap = n / p.Cout, co = n % p.Cout;
+            o = (((size_t)s * Ho + 2 * y + (tap >> 1)) * Wo + 2 * x + (tap & 1)) * p.Cout + co;
+        } else {
+            o = (((size_t)s * Ho + y) * Wo + x) * p.Cout + n;
+        }
+        *reinterpret_cast<float4*>(p.out + o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// head: planar [S][Cin][H][W] (+ optional shared noise-map plane as last channel) -> [S][H][W][64]
+// with v_in = (x - min) / range folded into the load (PnP_ADMM.m:121,177-182; no zero-range guard).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
+    extern __shared__ __align__(16) float hsm[];
+    const int Cin = p.Cin;
+    float* patch = hsm;                  // [Cin][18][18]
+    float* wts = hsm + Cin * 324;        // [9][Cin][64]
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.W + 15) / 16;
+    const int ty0 = (blockIdx.x / tiles_x) * 16, tx0 = (blockIdx.x % tiles_x) * 16;
+    const int s = blockIdx.z;
+    float mn = 0.f, inv = 1.f;
+    if (p.minmax) {
+        mn = p.minmax[2 * s];
+        inv = 1.0f / (p.minmax[2 * s + 1] - mn);
+    }
+    const int Cpl = p.noise_map ? Cin - 1 : Cin;  // channels stored in the planar input
+    for (int t = tid; t < Cin * 324; t += 256) {
+        int c = t / 324, r = t % 324;
+        int y = ty0 + r / 18 - 1, x = tx0 + r % 18 - 1;
+        float v = 0.f;
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+            if (c < Cpl) v = (__ldg(p.planar_in + (((size_t)s * Cpl + c) * p.H + y) * p.W + x) - mn) * inv;
+            else v = __ldg(p.noise_map + (size_t)y * p.W + x);
+        }
+        patch[t] = v;
+    }
+    for (int t = tid; t < 9 * Cin * 16; t += 256)
+        reinterpret_cast<float4*>(wts)[t] = __ldg(reinterpret_cast<const float4*>(p.w) + t);
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    const int y = ty0 + ty, x = tx0 + tx;
+    for (int cb = 0; cb < 64; cb += 16) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ry = tap / 3, sx = tap % 3;
+            for (int c = 0; c < Cin; ++c) {
+                float a = patch[c * 324 + (ty + ry) * 18 + tx + sx];
+                const float4* wp = reinterpret_cast<const float4*>(wts + (tap * Cin + c) * 64 + cb);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 b = wp[q];
+                    acc[4 * q + 0] = fmaf(a, b.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(a, b.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(a, b.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(a, b.w, acc[4 * q + 3]);
+                }
+            }
+        }
+        if (y < p.H && x < p.W) {
+            float4* o = reinterpret_cast<float4*>(p.nhwc + (((size_t)s * p.H + y) * p.W + x) * 64 + cb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// tail: [S][H][W][64] -> planar [S][10][H][W], v = out * range + min folded into the store
+// (PnP_ADMM.m:138,187-192).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tail_fp32_kernel(HeadTailParams p) {
+    __shared__ float patch[16][18][18 + 1];
+    __shared__ __align__(16) float wts[9][16][12];
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.W + 15) / 16;
+    const int ty0 = (blockIdx.x / tiles_x) * 16, tx0 = (blockIdx.x % tiles_x) * 16;
+    const int s = blockIdx.z;
+    const int ty = tid >> 4, tx = tid & 15;
+    const float* in = p.nhwc + (size_t)s * p.H * p.W * 64;
+    float acc[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) acc[j] = 0.f;
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        __syncthreads();
+        for (int t = tid; t < 324 * 4; t += 256) {
+            int pix = t >> 2, q = t & 3;
+            int py = pix / 18, px = pix % 18;
+            int y = ty0 + py - 1, x = tx0 + px - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < p.H && x >= 0 && x < p.W)
+                v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)y * p.W + x) * 64 + c0 + 4 * q));
+            patch[4 * q + 0][py][px] = v.x;
+            patch[4 * q + 1][py][px] = v.y;
+            patch[4 * q + 2][py][px] = v.z;
+            patch[4 * q + 3][py][px] = v.w;
+        }
+        for (int t = tid; t < 9 * 16 * 12; t += 256) {
+            int tap = t / 192, r = t % 192;
+            int k = r / 12, co = r % 12;
+            wts[tap][k][co] = co < 10 ? __ldg(p.w + ((size_t)tap * 64 + c0 + k) * 10 + co) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ry = tap / 3, sx = tap % 3;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                float a = patch[k][ty + ry][tx + sx];
+                float4 b0 = *reinterpret_cast<const float4*>(&wts[tap][k][0]);
+                float4 b1 = *reinterpret_cast<const float4*>(&wts[tap][k][4]);
+                float2 b2 = *reinterpret_cast<const float2*>(&wts[tap][k][8]);
+                acc[0] = fmaf(a, b0.x, acc[0]); acc[1] = fmaf(a, b0.y, acc[1]);
+                acc[2] = fmaf(a, b0.z, acc[2]); acc[3] = fmaf(a, b0.w, acc[3]);
+                acc[4] = fmaf(a, b1.x, acc[4]); acc[5] = fmaf(a, b1.y, acc[5]);
+                acc[6] = fmaf(a, b1.z, acc[6]); acc[7] = fmaf(a, b1.w, acc[7]);
+                acc[8] = fmaf(a, b2.x, acc[8]); acc[9] = fmaf(a, b2.y, acc[9]);
+            }
+        }
+    }
+    const int y = ty0 + ty, x = tx0 + tx;
+    if (y < p.H && x < p.W) {
+        float mn = 0.f, rg = 1.f;
+        if (p.minmax) {
+            mn = p.minmax[2 * s];
+            rg = p.minmax[2 * s + 1] - mn;
+        }
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+            p.planar_out[(((size_t)s * 10 + j) * p.H + y) * p.W + x] = acc[j] * rg + mn;
+    }
+}
+
+// planar affine kernels for the callback-denoiser path
+__global__ void normalize_kernel(const float* in, float* out, const float* minmax, size_t per_slice, int S, int undo) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int s = blockIdx.y;
+    if (i >= per_slice || s >= S) return;
+    float mn = minmax[2 * s];
+    float rg = minmax[2 * s + 1] - mn;
+    float v = in[(size_t)s * per_slice + i];
+    out[(size_t)s * per_slice + i] = undo ? v * rg + mn : (v - mn) / rg;
+}
+
+}  // namespace
+
+int conv3x3_fp32(qmri_ctx* ctx, const ConvParams& p) {
+    if (p.Cin % C3_KC || p.Cout % 64) return qmri_fail(QMRI_EINVAL, "conv3x3_fp32: Cin %% 8 / Cout %% 64");
+    dim3 grid(((p.H + 7) / 8) * ((p.W + 15) / 16), p.Cout / 64, p.S);
+    conv3x3_fp32_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+
+int resample_fp32(qmri_ctx* ctx, const ConvParams& p) {
+    const int up = p.mode;
+    const int64_t M = up ? (int64_t)p.S * p.H * p.W : (int64_t)p.S * (p.H / 2) * (p.W / 2);
+    const int N = up ? 4 * p.Cout : p.Cout;
+    if (p.Cin % 16 || N % 64) return qmri_fail(QMRI_EINVAL, "resample_fp32: Cin %% 16 / N %% 64");
+    dim3 grid((unsigned)((M + 63) / 64), N / 64);
+    resample_gemm_fp32_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+
+int head_fp32(qmri_ctx* ctx, const HeadTailParams& p) {
+    size_t smem = (size_t)(p.Cin * 324 + 9 * p.Cin * 64) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        QCUDA(cudaFuncSetAttribute(head_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(((p.H + 15) / 16) * ((p.W + 15) / 16), 1, p.S);
+    head_fp32_kernel<<<grid, 256, smem, ctx->stream>>>(p);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+
+int tail_fp32(qmri_ctx* ctx, const HeadTailParams& p) {
+    dim3 grid(((p.H + 15) / 16) * ((p.W + 15) / 16), 1, p.S);
+    tail_fp32_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+
+int normalize_planar(qmri_ctx* ctx, const float* in, float* out, const float* minmax, size_t per_slice, int S, int undo) {
+    dim3 grid((unsigned)((per_slice + 255) / 256), S);
+    normalize_kernel<<<grid, 256, 0, ctx->stream>>>(in, out, minmax, per_slice, S, undo);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}

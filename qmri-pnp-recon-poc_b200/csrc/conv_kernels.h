@@ -1,0 +1,34 @@
+// Host-visible interface of the K3 convolution kernels (conv_fp32.cu, conv_tc.cu).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+struct qmri_ctx;
+
+struct ConvParams {
+    const float* in;    // [S][H][W][Cin]
+    const float* w;     // packed weights (layout depends on the kernel, see unetres.cu)
+    float* out;         // [S][Ho][Wo][Cout]
+    const float* res1;  // optional residual, same shape as out (ResBlock input)
+    const float* res2;  // optional second residual (U-skip)
+    int S, H, W;        // input spatial size
+    int Cin, Cout;
+    int relu;
+    int mode;           // resample kernel: 0 = 2x2 s2 conv, 1 = 2x2 s2 transposed conv
+};
+
+struct HeadTailParams {
+    const float* planar_in;   // head: [S][Cpl][H][W]
+    const float* noise_map;   // head: optional [H][W] plane appended as the last input channel
+    float* planar_out;        // tail: [S][10][H][W]
+    float* nhwc;              // head: output [S][H][W][64]; tail: input
+    const float* w;           // head: [9][Cin][64]; tail: [9][64][10]
+    const float* minmax;      // optional [S][2] per-slice min / max (affine folded in)
+    int S, H, W, Cin;
+};
+
+int conv3x3_fp32(qmri_ctx* ctx, const ConvParams& p);
+int resample_fp32(qmri_ctx* ctx, const ConvParams& p);
+int head_fp32(qmri_ctx* ctx, const HeadTailParams& p);
+int tail_fp32(qmri_ctx* ctx, const HeadTailParams& p);
+int normalize_planar(qmri_ctx* ctx, const float* in, float* out, const float* minmax, size_t per_slice, int S, int undo);

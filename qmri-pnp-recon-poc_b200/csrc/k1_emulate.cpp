@@ -1,0 +1,176 @@
+// CPU emulation of the K1 kernel's control flow, thread by thread, using the very same
+// phase functions (xupdate_phases.cuh) and tables (op_tables.h) as the CUDA kernel.
+// TEST INFRASTRUCTURE: built into libk1emu.so by __graft_entry__.build() and driven by
+// tests/test_k1_emulation.py, because the build container has no GPU.  Never shipped in,
+// nor called by, libqmri_b200.so.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "op_tables.h"
+#include "xupdate_phases.cuh"
+
+using namespace k1;
+
+template <int MC>
+static void emulate(int mode, int C, int S, const optab::K1Tables& t, const float* in_re, const float* in_im,
+                    const float* v, const float* y, float rho, float* out_re, float* out_im, float* y_out,
+                    float* minmax) {
+    constexpr int THREADS = 8 * MC, CL = NF / MC, GROUPS = THREADS / 16, ROUNDS = MC / GROUPS, WPG = (MC + 31) / 32;
+    const float2* tw = reinterpret_cast<const float2*>(t.tw.data());
+    const size_t plane = (size_t)NF * NF;
+    for (int s = 0; s < S; ++s) {
+        float lmin = INFINITY, lmax = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+            const int f0 = t.frame_ptr[c], ns = t.frame_ptr[c + 1] - f0;
+            std::vector<std::vector<float2>> cols(CL, std::vector<float2>((size_t)MC * CS, float2{0, 0}));
+            std::vector<std::vector<float2>> pc(CL, std::vector<float2>(t.ns_max, float2{0, 0}));
+            const size_t base = ((size_t)(s * C + c)) * plane;
+            auto run_fft = [&](int r, bool inv) {
+                for (int rd = 0; rd < ROUNDS; ++rd) {
+                    std::vector<float2> regs((size_t)THREADS * 16);
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        float2* col = cols[r].data() + (rd * GROUPS + (tid >> 4)) * CS;
+                        float2(&a)[16] = *reinterpret_cast<float2(*)[16]>(&regs[(size_t)tid * 16]);
+                        if (inv) fft_s1_load<true>(col, tid & 15, tw, a);
+                        else fft_s1_load<false>(col, tid & 15, tw, a);
+                    }
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        float2* col = cols[r].data() + (rd * GROUPS + (tid >> 4)) * CS;
+                        fft_s1_store(col, tid & 15, *reinterpret_cast<float2(*)[16]>(&regs[(size_t)tid * 16]));
+                    }
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        float2* col = cols[r].data() + (rd * GROUPS + (tid >> 4)) * CS;
+                        if ((tid & 15) < 14) fft_s2_load(col, tid & 15, *reinterpret_cast<float2(*)[16]>(&regs[(size_t)tid * 16]));
+                    }
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        float2* col = cols[r].data() + (rd * GROUPS + (tid >> 4)) * CS;
+                        if ((tid & 15) < 14) {
+                            if (inv) fft_s2_store<true>(col, tid & 15, *reinterpret_cast<float2(*)[16]>(&regs[(size_t)tid * 16]));
+                            else fft_s2_store<false>(col, tid & 15, *reinterpret_cast<float2(*)[16]>(&regs[(size_t)tid * 16]));
+                        }
+                    }
+                }
+            };
+            if (mode != 3) {
+                for (int r = 0; r < CL; ++r) {
+                    const size_t slab = base + (size_t)r * MC * NF;
+                    for (int e = 0; e < MC * NF; ++e) {
+                        int mm = e / NF, n = e % NF;
+                        float re = in_re[slab + e], im = in_im ? in_im[slab + e] : 0.f;
+                        if (mode == 0) {
+                            re = 2.f * v[slab + e] - re;
+                            im = -im;
+                        }
+                        cols[r][mm * CS + n] = float2{re, im};
+                    }
+                    run_fft(r, false);
+                    for (int j = 0; j < ns; ++j) {
+                        uint16_t kk = t.samp[f0 + j];
+                        pc[r][j] = sampled_dft_partial<MC>(cols[r].data(), tw, r * MC, kk & 0xff, kk >> 8);
+                    }
+                }
+                const float inv_n = 1.0f / (float)NF;
+                std::vector<float2> cfull(t.ns_max);
+                for (int j = 0; j < ns; ++j) {
+                    float sx = 0.f, sy = 0.f;
+                    for (int r = 0; r < CL; ++r) {
+                        sx += pc[r][j].x;
+                        sy += pc[r][j].y;
+                    }
+                    sx *= inv_n;
+                    sy *= inv_n;
+                    size_t yi = (size_t)s * t.nmeas + f0 + j;
+                    if (mode == 2) {
+                        y_out[2 * yi] = sx;
+                        y_out[2 * yi + 1] = sy;
+                    } else {
+                        float g = (1.0f / (1.0f + rho)) * inv_n;
+                        cfull[j] = float2{(y[2 * yi] - sx) * g, (y[2 * yi + 1] - sy) * g};
+                    }
+                }
+                if (mode == 2) continue;
+                for (int r = 0; r < CL; ++r) pc[r] = cfull;
+            } else {
+                const float inv_n = 1.0f / (float)NF;
+                for (int r = 0; r < CL; ++r)
+                    for (int j = 0; j < ns; ++j) {
+                        size_t yi = (size_t)s * t.nmeas + f0 + j;
+                        pc[r][j] = float2{y[2 * yi] * inv_n, y[2 * yi + 1] * inv_n};
+                    }
+            }
+            for (int r = 0; r < CL; ++r) {
+                for (int tid = 0; tid < THREADS; ++tid) {
+                    int warp = tid >> 5, lane = tid & 31;
+                    int g = warp / WPG, mm = (warp % WPG) * 32 + lane;
+                    if (mm < MC && g < NROWGRP) {
+                        const uint16_t* row_ptr = t.row_ptr.data() + (size_t)c * (NF + 1);
+                        int r0 = t.row_grp[c * (NROWGRP + 1) + g], r1 = t.row_grp[c * (NROWGRP + 1) + g + 1];
+                        sparse_idft_rows(cols[r].data() + mm * CS, pc[r].data(), tw, row_ptr, t.rowtab.data() + f0,
+                                         r * MC + mm, r0, r1);
+                    }
+                }
+                run_fft(r, true);
+                const size_t slab = base + (size_t)r * MC * NF;
+                for (int e = 0; e < MC * NF; ++e) {
+                    int mm = e / NF, n = e % NF;
+                    float2 cr = cols[r][mm * CS + n];
+                    float ore, oim;
+                    if (mode == 0) {
+                        ore = v[slab + e] + cr.x;
+                        oim = cr.y;
+                    } else if (mode == 1) {
+                        ore = in_re[slab + e] + cr.x;
+                        oim = (in_im ? in_im[slab + e] : 0.f) + cr.y;
+                    } else {
+                        ore = cr.x;
+                        oim = cr.y;
+                    }
+                    out_re[slab + e] = ore;
+                    out_im[slab + e] = oim;
+                    lmin = fminf(lmin, ore);
+                    lmax = fmaxf(lmax, ore);
+                }
+            }
+        }
+        if (minmax) {
+            minmax[2 * s] = lmin;
+            minmax[2 * s + 1] = lmax;
+        }
+    }
+}
+
+extern "C" {
+
+// pattern: 0 = spiral(S_curve = (int)arg), 1 = epi(percentage = arg).  Returns nmeas; fills idx/frame_ptr when non-null.
+int k1emu_masks(int pattern, int N, double arg, int L, int32_t* idx, int64_t* frame_ptr) {
+    std::vector<std::vector<int32_t>> frames;
+    if (pattern == 0) optab::spiral_frames(N, (int)arg, L, frames);
+    else optab::epi_frames(N, N, arg, L, frames);
+    int64_t n = 0;
+    for (int f = 0; f < L; ++f) {
+        if (frame_ptr) frame_ptr[f] = n;
+        for (int32_t k : frames[f]) {
+            if (idx) idx[n] = k;
+            ++n;
+        }
+    }
+    if (frame_ptr) frame_ptr[L] = n;
+    return (int)n;
+}
+
+// mode: 0 ADMM (in = w, v given, out = w'), 1 SOLVE (in = z, out = x), 2 FORWARD (in = x, y_out), 3 ADJOINT (y, out)
+int k1emu_run(int mode, int mc, int pattern, double arg, int C, int S, const float* in_re, const float* in_im,
+              const float* v, const float* y, float rho, float* out_re, float* out_im, float* y_out, float* minmax) {
+    std::vector<std::vector<int32_t>> frames;
+    if (pattern == 0) optab::spiral_frames(NF, (int)arg, C, frames);
+    else optab::epi_frames(NF, NF, arg, C, frames);
+    optab::K1Tables t;
+    optab::build_k1_tables(NF, frames, t);
+    if (mc == 56) emulate<56>(mode, C, S, t, in_re, in_im, v, y, rho, out_re, out_im, y_out, minmax);
+    else emulate<28>(mode, C, S, t, in_re, in_im, v, y, rho, out_re, out_im, y_out, minmax);
+    return t.nmeas;
+}
+}

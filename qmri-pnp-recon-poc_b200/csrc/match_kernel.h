@@ -1,0 +1,35 @@
+// Host-visible interface of the K2 kernels (see match_kernel.cu).
+#pragma once
+#include <stdint.h>
+
+struct qmri_ctx;
+
+struct K2Params {
+    const float* x_re;   // [C][npix] planar pixel signatures
+    const float* x_im;   // may be null (real data)
+    int64_t npix;
+    const float* Dp;     // [K][CP] atoms, rows padded with zeros to CP = 4*ceil(C/4)
+    int64_t a0, a1;      // atom range scored by this launch
+    unsigned long long* keys;  // [npix], zero-initialised by the caller
+    int C, CP;
+};
+
+struct K2Finish {
+    const float* x_re;
+    const float* x_im;
+    int64_t npix;
+    const float* Dp;
+    const float* normD;  // [K]
+    const float* lut;    // [Q][K] (column-major K x Q)
+    int64_t K;
+    int C, CP, Q;
+    const unsigned long long* keys;
+    float* qmap;         // [Q][npix]
+    float* pd;           // [npix][2]
+    float* mt;           // [npix]
+    int32_t* dm;         // [npix], 1-based
+};
+
+int k2_padded_channels(int C);
+int k2_launch_keys(qmri_ctx* ctx, const K2Params& p);
+int k2_launch_finish(qmri_ctx* ctx, const K2Finish& p);

@@ -1,0 +1,133 @@
+// Host-side construction of the acquisition operator: sampling masks and the lookup
+// tables the K1 kernel walks.  Header-only so the CPU emulation of K1 can share it.
+//
+// Mask constructors follow (maths only; written from scratch in C++):
+//   main_files/subsampling_patterns/setup_subsampling_spiralgrided.m:7-34
+//   main_files/subsampling_patterns/setup_subsampling_epi.m:20-30
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace optab {
+
+// MATLAB round(): halves away from zero
+static inline double matlab_round(double x) { return x < 0 ? -floor(-x + 0.5) : floor(x + 0.5); }
+
+// frames[i] = ascending 0-based column-major indices n + N*m (MATLAB find order - 1)
+static inline void spiral_frames(int N, int S, int L, std::vector<std::vector<int32_t>>& frames) {
+    const double PI = 3.14159265358979323846;
+    const double delta = PI / 180.0 * 7.5;
+    std::vector<double> theta(S), r(S);
+    double rmin = 1e300, rmax = -1e300;
+    for (int i = 0; i < S; ++i) {
+        // linspace(0, 2*pi, S): MATLAB computes d1 + (0:n1)*(d2-d1)/n1 and pins the last point
+        double t = (S > 1) ? (double)i * (2.0 * PI) / (double)(S - 1) : 2.0 * PI;
+        if (i == S - 1) t = 2.0 * PI;
+        theta[i] = 8.0 * t;
+        r[i] = pow(1.05, theta[i]);
+        rmin = std::min(rmin, r[i]);
+        rmax = std::max(rmax, r[i]);
+    }
+    for (int i = 0; i < S; ++i) r[i] = (r[i] - rmin) / (rmax - rmin);
+    frames.assign(L, {});
+    std::vector<uint8_t> img((size_t)N * N);
+    for (int f = 0; f < L; ++f) {
+        std::fill(img.begin(), img.end(), 0);
+        for (int i = 0; i < S; ++i) {
+            double cx = r[i] * cos(theta[i] + f * delta);
+            double cy = r[i] * sin(theta[i] + f * delta);
+            double gx = matlab_round(cx * N / 2) + N / 2 + 1;
+            double gy = matlab_round(cy * N / 2) + N / 2 + 1;
+            gx = std::min(gx, (double)N);
+            gy = std::min(gy, (double)N);
+            int n = (int)gx - 1, m = (int)gy - 1;  // 0-based (row, col)
+            // fftshift of an even-sized image: circular shift by N/2 in both dims
+            int ns = (n + N / 2) % N, ms = (m + N / 2) % N;
+            img[(size_t)ms * N + ns] = 1;
+        }
+        for (int k = 0; k < N * N; ++k)
+            if (img[k]) frames[f].push_back(k);
+    }
+}
+
+static inline void epi_frames(int N, int M, double percentage, int L, std::vector<std::vector<int32_t>>& frames) {
+    int step = (int)matlab_round(1.0 / percentage);
+    int no_of_steps = N / step;
+    std::vector<uint8_t> comb(N, 0);
+    for (int i = 0; i < step * no_of_steps; i += step) comb[i] = 1;
+    frames.assign(L, {});
+    for (int f = 0; f < L; ++f) {
+        std::vector<uint8_t> sh(N);
+        for (int n = 0; n < N; ++n) sh[(n + 1) % N] = comb[n];  // comb([N,1:N-1])
+        comb = sh;
+        for (int m = 0; m < M; ++m)
+            for (int n = 0; n < N; ++n)
+                if (comb[n]) frames[f].push_back(n + N * m);
+    }
+}
+
+struct K1Tables {
+    int C = 0, nmeas = 0, ns_max = 0;
+    std::vector<int> frame_ptr;       // [C+1]
+    std::vector<int32_t> idx;         // [nmeas]
+    std::vector<uint16_t> samp;       // [nmeas]
+    std::vector<uint16_t> row_ptr;    // [C][225]
+    std::vector<uint32_t> rowtab;     // [nmeas]
+    std::vector<int> row_grp;         // [C][8]
+    std::vector<float> tw;            // [224][2]
+};
+
+static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t) {
+    const int NG = 7;
+    t.C = (int)frames.size();
+    t.frame_ptr.assign(t.C + 1, 0);
+    for (int c = 0; c < t.C; ++c) t.frame_ptr[c + 1] = t.frame_ptr[c] + (int)frames[c].size();
+    t.nmeas = t.frame_ptr[t.C];
+    t.ns_max = 0;
+    t.idx.clear();
+    t.samp.clear();
+    t.row_ptr.assign((size_t)t.C * (N + 1), 0);
+    t.rowtab.assign(t.nmeas, 0);
+    t.row_grp.assign((size_t)t.C * (NG + 1), 0);
+    for (int c = 0; c < t.C; ++c) {
+        const auto& f = frames[c];
+        int ns = (int)f.size();
+        t.ns_max = std::max(t.ns_max, ns);
+        std::vector<int> cnt(N + 1, 0);
+        for (int j = 0; j < ns; ++j) {
+            int k1 = f[j] % N, k2 = f[j] / N;
+            t.idx.push_back(f[j]);
+            t.samp.push_back((uint16_t)(k1 | (k2 << 8)));
+            cnt[k1 + 1]++;
+        }
+        uint16_t* rp = &t.row_ptr[(size_t)c * (N + 1)];
+        rp[0] = 0;
+        for (int k = 0; k < N; ++k) rp[k + 1] = (uint16_t)(rp[k] + cnt[k + 1]);
+        std::vector<int> fill(rp, rp + N);
+        for (int j = 0; j < ns; ++j) {  // ascending j keeps k2 ascending inside a row
+            int k1 = f[j] % N, k2 = f[j] / N;
+            t.rowtab[t.frame_ptr[c] + fill[k1]++] = (uint32_t)k2 | ((uint32_t)j << 8);
+        }
+        // contiguous row ranges with balanced cost (1 per row + 1 per sample)
+        double total = N + ns, acc = 0;
+        int* rg = &t.row_grp[(size_t)c * (NG + 1)];
+        int g = 1;
+        rg[0] = 0;
+        for (int k = 0; k < N && g < NG; ++k) {
+            acc += 1 + cnt[k + 1];
+            if (acc >= total * g / NG) rg[g++] = k + 1;
+        }
+        while (g <= NG) rg[g++] = N;
+    }
+    t.tw.resize(2 * N);
+    const double PI = 3.14159265358979323846;
+    for (int i = 0; i < N; ++i) {
+        t.tw[2 * i] = (float)cos(-2.0 * PI * i / N);
+        t.tw[2 * i + 1] = (float)sin(-2.0 * PI * i / N);
+    }
+}
+
+}  // namespace optab

@@ -1,0 +1,894 @@
+// libqmri_b200 - the C ABI of include/qmri.h: context, acquisition operator, x-update,
+// ADMM loop driver, denoiser and dictionary-matching entry points.  Each entry point's
+// reference counterpart is cited in include/qmri.h.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_kernels.h"
+#include "match_kernel.h"
+#include "op_tables.h"
+#include "unetres.h"
+#include "xupdate_kernel.h"
+
+thread_local char g_qmri_err[512] = "";
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n) {
+        if (n <= bytes) return QMRI_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) return qmri_fail(QMRI_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+        bytes = n;
+        return QMRI_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+namespace {
+
+// host-layout array (already on the device as raw bytes) -> planar fp32
+template <typename T>
+__global__ void unpack_kernel(const T* __restrict__ src, float* __restrict__ re, float* __restrict__ im, size_t n, int cplx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (cplx) {
+        re[i] = (float)src[2 * i];
+        if (im) im[i] = (float)src[2 * i + 1];
+    } else {
+        re[i] = (float)src[i];
+        if (im) im[i] = 0.f;
+    }
+}
+template <typename T>
+__global__ void pack_kernel(T* __restrict__ dst, const float* __restrict__ re, const float* __restrict__ im, size_t n, int cplx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (cplx) {
+        dst[2 * i] = (T)re[i];
+        dst[2 * i + 1] = im ? (T)im[i] : (T)0;
+    } else {
+        dst[i] = (T)re[i];
+    }
+}
+// interleaved complex <-> float2
+template <typename T>
+__global__ void cvt_c_in_kernel(const T* __restrict__ src, float2* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_float2((float)src[2 * i], (float)src[2 * i + 1]);
+}
+template <typename T>
+__global__ void cvt_c_out_kernel(T* __restrict__ dst, const float2* __restrict__ src, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        dst[2 * i] = (T)src[i].x;
+        dst[2 * i + 1] = (T)src[i].y;
+    }
+}
+// z = v - u (u optional)
+__global__ void sub_kernel(const float* vr, const float* vi, const float* ur, const float* ui, float* zr, float* zi, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    zr[i] = vr[i] - (ur ? ur[i] : 0.f);
+    zi[i] = (vi ? vi[i] : 0.f) - (ui ? ui[i] : 0.f);
+}
+// w = x + u (u optional) with per-slice min/max of Re(w); w may be null (min/max only)
+__global__ void add_minmax_kernel(const float* xr, const float* xi, const float* ur, const float* ui, float* wr, float* wi,
+                                  size_t per_slice, int* minmax) {
+    __shared__ float smin[8], smax[8];
+    const int s = blockIdx.y;
+    float lmin = INFINITY, lmax = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_slice; i += (size_t)gridDim.x * blockDim.x) {
+        size_t g = (size_t)s * per_slice + i;
+        float a = xr[g] + (ur ? ur[g] : 0.f);
+        if (wr) {
+            wr[g] = a;
+            wi[g] = xi[g] + (ui ? ui[g] : 0.f);
+        }
+        lmin = fminf(lmin, a);
+        lmax = fmaxf(lmax, a);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        smin[threadIdx.x >> 5] = lmin;
+        smax[threadIdx.x >> 5] = lmax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && minmax) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            lmin = fminf(lmin, smin[w]);
+            lmax = fmaxf(lmax, smax[w]);
+        }
+        atomicMin(minmax + 2 * s, float_to_ordered(lmin));
+        atomicMax(minmax + 2 * s + 1, float_to_ordered(lmax));
+    }
+}
+// ordered-int keys -> floats, and re-arm the keys for the next iteration
+__global__ void minmax_finalize_kernel(int* ord, float* mm, int S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S) {
+        mm[2 * i] = ordered_to_float(ord[2 * i]);
+        mm[2 * i + 1] = ordered_to_float(ord[2 * i + 1]);
+        ord[2 * i] = 0x7fffffff;
+        ord[2 * i + 1] = (int)0x80000000;
+    }
+}
+
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+int unpack_async(qmri_ctx* ctx, const void* dev_raw, int dtype, float* re, float* im, size_t n) {
+    if (n == 0) return QMRI_OK;
+    int cplx = dtype_is_complex(dtype);
+    if (dtype == QMRI_F32 || dtype == QMRI_C64)
+        unpack_kernel<float><<<nblk(n), 256, 0, ctx->stream>>>((const float*)dev_raw, re, im, n, cplx);
+    else
+        unpack_kernel<double><<<nblk(n), 256, 0, ctx->stream>>>((const double*)dev_raw, re, im, n, cplx);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+int pack_async(qmri_ctx* ctx, void* dev_raw, int dtype, const float* re, const float* im, size_t n) {
+    if (n == 0) return QMRI_OK;
+    int cplx = dtype_is_complex(dtype);
+    if (dtype == QMRI_F32 || dtype == QMRI_C64)
+        pack_kernel<float><<<nblk(n), 256, 0, ctx->stream>>>((float*)dev_raw, re, im, n, cplx);
+    else
+        pack_kernel<double><<<nblk(n), 256, 0, ctx->stream>>>((double*)dev_raw, re, im, n, cplx);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+
+bool valid_dtype(int dt) { return dt >= QMRI_F32 && dt <= QMRI_C128; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int qmri_version(void) { return QMRI_VERSION; }
+extern "C" const char* qmri_last_error(void) { return g_qmri_err; }
+
+extern "C" int qmri_ctx_create(qmri_ctx** out, int device_id) {
+    if (!out) return qmri_fail(QMRI_EINVAL, "qmri_ctx_create: out is null");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return qmri_fail(QMRI_ECUDA, "no CUDA device available (%s); libqmri_b200 has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= ndev) return qmri_fail(QMRI_EINVAL, "device %d out of range [0,%d)", device_id, ndev);
+    cudaDeviceProp prop;
+    QCUDA(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10)
+        return qmri_fail(QMRI_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device_id,
+                         prop.major, prop.minor);
+    qmri_ctx* ctx = new qmri_ctx();
+    ctx->device = device_id;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    DevSetter ds(device_id);
+    QCUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    *out = ctx;
+    return QMRI_OK;
+}
+extern "C" int qmri_ctx_destroy(qmri_ctx* ctx) {
+    if (!ctx) return QMRI_OK;
+    DevSetter ds(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return QMRI_OK;
+}
+extern "C" int qmri_ctx_set_stream(qmri_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return qmri_fail(QMRI_EINVAL, "null ctx");
+    DevSetter ds(ctx->device);
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        QCUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return QMRI_OK;
+}
+extern "C" int qmri_ctx_synchronize(qmri_ctx* ctx) {
+    if (!ctx) return qmri_fail(QMRI_EINVAL, "null ctx");
+    DevSetter ds(ctx->device);
+    QCUDA(cudaStreamSynchronize(ctx->stream));
+    return QMRI_OK;
+}
+extern "C" int64_t qmri_ctx_launch_count(qmri_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// acquisition operator
+// ------------------------------------------------------------------------------------------
+struct qmri_op {
+    qmri_ctx* ctx = nullptr;
+    int N = 0, M = 0, C = 0, L = 0;
+    int k1_mc = 28;
+    optab::K1Tables t;
+    // device tables
+    float2* d_tw = nullptr;
+    int* d_frame_ptr = nullptr;
+    uint16_t* d_samp = nullptr;
+    uint16_t* d_row_ptr = nullptr;
+    uint32_t* d_rowtab = nullptr;
+    int* d_row_grp = nullptr;
+    // scratch for the host entry points
+    DevBuf stage, a_re, a_im, b_re, b_im, c_re, c_im, ybuf, mm_ord, mm_f;
+    size_t plane() const { return (size_t)N * M * C; }
+};
+
+static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::vector<std::vector<int32_t>>& frames,
+                          const double* V, qmri_op** out) {
+    if (!ctx || !out) return qmri_fail(QMRI_EINVAL, "operator: null argument");
+    if (N != 224 || M != 224)
+        return qmri_fail(QMRI_EUNSUPPORTED, "this build supports N == M == 224 only (got %d x %d)", N, M);
+    if (C < 1 || C > 64) return qmri_fail(QMRI_EINVAL, "C = %d out of range", C);
+    if (L != C) return qmri_fail(QMRI_EUNSUPPORTED, "unsupported V: %d x %d; this build needs V == eye(C) (SURVEY.md 8f-2)", L, C);
+    if (V) {
+        for (int i = 0; i < L; ++i)
+            for (int c = 0; c < C; ++c)
+                if (fabs(V[i + (size_t)L * c] - (i == c ? 1.0 : 0.0)) > 1e-12)
+                    return qmri_fail(QMRI_EUNSUPPORTED, "unsupported V: not the identity at (%d,%d); general V is SURVEY.md 8f-2", i + 1, c + 1);
+    }
+    for (int f = 0; f < L; ++f) {
+        if (frames[f].size() > 4096) return qmri_fail(QMRI_EUNSUPPORTED, "frame %d samples %zu k-space locations; limit 4096", f, frames[f].size());
+        for (size_t j = 0; j < frames[f].size(); ++j) {
+            if (frames[f][j] < 0 || frames[f][j] >= N * M) return qmri_fail(QMRI_EINVAL, "k index out of range in frame %d", f);
+            if (j && frames[f][j] <= frames[f][j - 1]) return qmri_fail(QMRI_EINVAL, "k indices must ascend inside frame %d", f);
+        }
+    }
+    DevSetter ds(ctx->device);
+    qmri_op* op = new qmri_op();
+    op->ctx = ctx;
+    op->N = N; op->M = M; op->C = C; op->L = L;
+    const char* env = getenv("QMRI_K1_MC");
+    if (env && atoi(env) == 56) op->k1_mc = 56;
+    optab::build_k1_tables(N, frames, op->t);
+    const optab::K1Tables& t = op->t;
+    size_t nm = std::max(1, t.nmeas);
+    int r = 0;
+    r |= dev_alloc(&op->d_tw, (size_t)N);
+    r |= dev_alloc(&op->d_frame_ptr, (size_t)C + 1);
+    r |= dev_alloc(&op->d_samp, nm);
+    r |= dev_alloc(&op->d_row_ptr, t.row_ptr.size());
+    r |= dev_alloc(&op->d_rowtab, nm);
+    r |= dev_alloc(&op->d_row_grp, t.row_grp.size());
+    if (r) {
+        qmri_op_destroy(op);
+        return QMRI_ENOMEM;
+    }
+    cudaMemcpy(op->d_tw, t.tw.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_frame_ptr, t.frame_ptr.data(), sizeof(int) * (C + 1), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_samp, t.samp.data(), sizeof(uint16_t) * t.nmeas, cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_row_ptr, t.row_ptr.data(), sizeof(uint16_t) * t.row_ptr.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_rowtab, t.rowtab.data(), sizeof(uint32_t) * t.nmeas, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(op->d_row_grp, t.row_grp.data(), sizeof(int) * t.row_grp.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        qmri_op_destroy(op);
+        return qmri_fail(QMRI_ECUDA, "operator table upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = op;
+    return QMRI_OK;
+}
+
+extern "C" int qmri_op_spiral(qmri_ctx* ctx, int N, int M, int S_curve, const double* V, int L, int C, qmri_op** out) {
+    if (N != M) return qmri_fail(QMRI_EINVAL, "setup_subsampling_spiralgrided assumes N == M (zeros(N), line 31)");
+    if (S_curve < 2 || L < 1) return qmri_fail(QMRI_EINVAL, "spiral: need S >= 2 and L >= 1");
+    std::vector<std::vector<int32_t>> frames;
+    optab::spiral_frames(N, S_curve, L, frames);
+    return op_from_frames(ctx, N, M, C, L, frames, V, out);
+}
+extern "C" int qmri_op_epi(qmri_ctx* ctx, int N, int M, double percentage, const double* V, int L, int C, qmri_op** out) {
+    if (!(percentage > 0.0) || percentage > 1.0 || L < 1) return qmri_fail(QMRI_EINVAL, "epi: percentage must be in (0,1]");
+    std::vector<std::vector<int32_t>> frames;
+    optab::epi_frames(N, M, percentage, L, frames);
+    return op_from_frames(ctx, N, M, C, L, frames, V, out);
+}
+extern "C" int qmri_op_create(qmri_ctx* ctx, int N, int M, int C, int L, const int32_t* idx, const int64_t* frame_ptr,
+                              const double* V, qmri_op** out) {
+    if (!idx || !frame_ptr || L < 1) return qmri_fail(QMRI_EINVAL, "qmri_op_create: null idx / frame_ptr");
+    std::vector<std::vector<int32_t>> frames(L);
+    for (int f = 0; f < L; ++f) {
+        if (frame_ptr[f + 1] < frame_ptr[f]) return qmri_fail(QMRI_EINVAL, "frame_ptr must be non-decreasing");
+        frames[f].assign(idx + frame_ptr[f], idx + frame_ptr[f + 1]);
+    }
+    return op_from_frames(ctx, N, M, C, L, frames, V, out);
+}
+extern "C" int qmri_op_destroy(qmri_op* op) {
+    if (!op) return QMRI_OK;
+    DevSetter ds(op->ctx->device);
+    cudaStreamSynchronize(op->ctx->stream);
+    cudaFree(op->d_tw); cudaFree(op->d_frame_ptr); cudaFree(op->d_samp);
+    cudaFree(op->d_row_ptr); cudaFree(op->d_rowtab); cudaFree(op->d_row_grp);
+    op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
+    op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
+    delete op;
+    return QMRI_OK;
+}
+extern "C" int64_t qmri_op_nmeas(const qmri_op* op) { return op ? op->t.nmeas : -1; }
+extern "C" int qmri_op_indices(const qmri_op* op, int32_t* idx, int64_t* frame_ptr) {
+    if (!op) return qmri_fail(QMRI_EINVAL, "null op");
+    if (idx) memcpy(idx, op->t.idx.data(), sizeof(int32_t) * op->t.nmeas);
+    if (frame_ptr)
+        for (int f = 0; f <= op->L; ++f) frame_ptr[f] = op->t.frame_ptr[f];
+    return QMRI_OK;
+}
+
+static void k1_fill_tables(const qmri_op* op, K1Params& p) {
+    p.tw = op->d_tw;
+    p.frame_ptr = op->d_frame_ptr;
+    p.samp = op->d_samp;
+    p.row_ptr = op->d_row_ptr;
+    p.rowtab = op->d_rowtab;
+    p.row_grp = op->d_row_grp;
+    p.C = op->C;
+    p.nmeas = op->t.nmeas;
+}
+
+static int y_upload(qmri_op* op, const void* y, int y_dtype, int S) {
+    qmri_ctx* ctx = op->ctx;
+    if (!dtype_is_complex(y_dtype)) return qmri_fail(QMRI_EINVAL, "measurements y must be complex (QMRI_C64 / QMRI_C128)");
+    size_t n = (size_t)S * op->t.nmeas;
+    QCHECK(op->ybuf.ensure(std::max<size_t>(n, 1) * sizeof(float2)));
+    QCHECK(op->stage.ensure(std::max<size_t>(n, 1) * dtype_size(y_dtype)));
+    if (n == 0) return QMRI_OK;
+    QCUDA(cudaMemcpyAsync(op->stage.p, y, n * dtype_size(y_dtype), cudaMemcpyHostToDevice, ctx->stream));
+    if (y_dtype == QMRI_C64) cvt_c_in_kernel<float><<<nblk(n), 256, 0, ctx->stream>>>((const float*)op->stage.p, op->ybuf.as<float2>(), n);
+    else cvt_c_in_kernel<double><<<nblk(n), 256, 0, ctx->stream>>>((const double*)op->stage.p, op->ybuf.as<float2>(), n);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+
+// H2D of a host N x M x C x S array into planar fp32 (re, im)
+static int image_upload(qmri_op* op, const void* x, int dtype, int S, DevBuf& re, DevBuf& im) {
+    qmri_ctx* ctx = op->ctx;
+    size_t n = op->plane() * S;
+    QCHECK(re.ensure(n * sizeof(float)));
+    QCHECK(im.ensure(n * sizeof(float)));
+    QCHECK(op->stage.ensure(n * dtype_size(dtype)));
+    QCUDA(cudaMemcpyAsync(op->stage.p, x, n * dtype_size(dtype), cudaMemcpyHostToDevice, ctx->stream));
+    return unpack_async(ctx, op->stage.p, dtype, re.as<float>(), im.as<float>(), n);
+}
+static int image_download(qmri_op* op, void* x, int dtype, int S, const float* re, const float* im) {
+    qmri_ctx* ctx = op->ctx;
+    size_t n = op->plane() * S;
+    QCHECK(op->stage.ensure(n * dtype_size(dtype)));
+    QCHECK(pack_async(ctx, op->stage.p, dtype, re, im, n));
+    QCUDA(cudaMemcpyAsync(x, op->stage.p, n * dtype_size(dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    QCUDA(cudaStreamSynchronize(ctx->stream));
+    return QMRI_OK;
+}
+
+extern "C" int qmri_forward(qmri_op* op, const void* x, int x_dtype, int S, void* y, int y_dtype) {
+    if (!op || !x || !y) return qmri_fail(QMRI_EINVAL, "qmri_forward: null argument");
+    if (S < 0 || !valid_dtype(x_dtype) || !dtype_is_complex(y_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_forward: bad S / dtype");
+    if (S == 0) return QMRI_OK;
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    QCHECK(image_upload(op, x, x_dtype, S, op->a_re, op->a_im));
+    size_t n = (size_t)S * op->t.nmeas;
+    QCHECK(op->ybuf.ensure(std::max<size_t>(n, 1) * sizeof(float2)));
+    K1Params p = {};
+    k1_fill_tables(op, p);
+    p.mode = K1_FORWARD;
+    p.in_re = op->a_re.as<float>();
+    p.in_im = dtype_is_complex(x_dtype) ? op->a_im.as<float>() : nullptr;
+    p.y_out = op->ybuf.as<float2>();
+    QCHECK(k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc));
+    if (n) {
+        QCHECK(op->stage.ensure(n * dtype_size(y_dtype)));
+        if (y_dtype == QMRI_C64) cvt_c_out_kernel<float><<<nblk(n), 256, 0, ctx->stream>>>((float*)op->stage.p, op->ybuf.as<float2>(), n);
+        else cvt_c_out_kernel<double><<<nblk(n), 256, 0, ctx->stream>>>((double*)op->stage.p, op->ybuf.as<float2>(), n);
+        QLAUNCH_CHECK(ctx);
+        QCUDA(cudaMemcpyAsync(y, op->stage.p, n * dtype_size(y_dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    QCUDA(cudaStreamSynchronize(ctx->stream));
+    return QMRI_OK;
+}
+
+extern "C" int qmri_adjoint(qmri_op* op, const void* y, int y_dtype, int S, void* x, int x_dtype) {
+    if (!op || !y || !x) return qmri_fail(QMRI_EINVAL, "qmri_adjoint: null argument");
+    if (S < 0 || !dtype_is_complex(x_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_adjoint: x must be complex");
+    if (S == 0) return QMRI_OK;
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    QCHECK(y_upload(op, y, y_dtype, S));
+    size_t n = op->plane() * S;
+    QCHECK(op->a_re.ensure(n * sizeof(float)));
+    QCHECK(op->a_im.ensure(n * sizeof(float)));
+    K1Params p = {};
+    k1_fill_tables(op, p);
+    p.mode = K1_ADJOINT;
+    p.y = op->ybuf.as<float2>();
+    p.out_re = op->a_re.as<float>();
+    p.out_im = op->a_im.as<float>();
+    QCHECK(k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc));
+    return image_download(op, x, x_dtype, S, op->a_re.as<float>(), op->a_im.as<float>());
+}
+
+extern "C" int qmri_xupdate(qmri_op* op, double rho, const void* y, int y_dtype, const void* v, int v_dtype, const void* u,
+                            int u_dtype, int S, void* x, int x_dtype, void* w, int w_dtype, float* minmax) {
+    if (!op || !y || !v || !x) return qmri_fail(QMRI_EINVAL, "qmri_xupdate: null argument");
+    if (S < 0 || !valid_dtype(v_dtype) || !dtype_is_complex(x_dtype) || (u && !valid_dtype(u_dtype)) || (w && !dtype_is_complex(w_dtype)))
+        return qmri_fail(QMRI_EINVAL, "qmri_xupdate: bad S / dtype");
+    if (!(rho > 0.0)) return qmri_fail(QMRI_EINVAL, "qmri_xupdate: rho must be positive");
+    if (S == 0) return QMRI_OK;
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    size_t n = op->plane() * S;
+    QCHECK(y_upload(op, y, y_dtype, S));
+    QCHECK(image_upload(op, v, v_dtype, S, op->a_re, op->a_im));                 // a = v
+    if (u) QCHECK(image_upload(op, u, u_dtype, S, op->b_re, op->b_im));           // b = u
+    QCHECK(op->c_re.ensure(n * sizeof(float)));
+    QCHECK(op->c_im.ensure(n * sizeof(float)));
+    float *ar = op->a_re.as<float>(), *ai = op->a_im.as<float>();
+    float *br = u ? op->b_re.as<float>() : nullptr, *bi = u ? op->b_im.as<float>() : nullptr;
+    float *cr = op->c_re.as<float>(), *ci = op->c_im.as<float>();
+    sub_kernel<<<nblk(n), 256, 0, ctx->stream>>>(ar, ai, br, bi, cr, ci, n);     // c = z = v - u
+    QLAUNCH_CHECK(ctx);
+    K1Params p = {};
+    k1_fill_tables(op, p);
+    p.mode = K1_SOLVE;
+    p.in_re = cr; p.in_im = ci;
+    p.y = op->ybuf.as<float2>();
+    p.out_re = ar; p.out_im = ai;                                                // a = x
+    p.inv_1p_rho = (float)(1.0 / (1.0 + rho));
+    QCHECK(k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc));
+    QCHECK(image_download(op, x, x_dtype, S, ar, ai));
+    if (w || minmax) {
+        QCHECK(op->mm_ord.ensure(2 * S * sizeof(int)));
+        QCHECK(op->mm_f.ensure(2 * S * sizeof(float)));
+        QCHECK(k1_minmax_init(ctx, op->mm_ord.as<int>(), S));
+        dim3 grid(std::min<unsigned>(nblk(op->plane()), 256), S);
+        add_minmax_kernel<<<grid, 256, 0, ctx->stream>>>(ar, ai, br, bi, cr, ci, op->plane(), op->mm_ord.as<int>());  // c = w
+        QLAUNCH_CHECK(ctx);
+        minmax_finalize_kernel<<<nblk(S, 128), 128, 0, ctx->stream>>>(op->mm_ord.as<int>(), op->mm_f.as<float>(), S);
+        QLAUNCH_CHECK(ctx);
+        if (w) QCHECK(image_download(op, w, w_dtype, S, cr, ci));
+        if (minmax) {
+            QCUDA(cudaMemcpyAsync(minmax, op->mm_f.p, 2 * S * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            QCUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return QMRI_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// denoiser entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int qmri_unetres_load(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_weights, qmri_net** out) {
+    return unetres_create(ctx, in_nc, weights, n_weights, out);
+}
+extern "C" int qmri_unetres_destroy(qmri_net* net) {
+    if (net) {
+        DevSetter ds(net->ctx->device);
+        cudaStreamSynchronize(net->ctx->stream);
+    }
+    unetres_free(net);
+    return QMRI_OK;
+}
+extern "C" int qmri_unetres_set_precision(qmri_net* net, int mode) {
+    if (!net) return qmri_fail(QMRI_EINVAL, "null net");
+    if (mode != 0) return qmri_fail(QMRI_EUNSUPPORTED, "denoiser precision mode %d is not available in this build", mode);
+    net->precision = mode;
+    return QMRI_OK;
+}
+extern "C" double qmri_unetres_flops(const qmri_net* net, int S, int H, int W) {
+    return net ? unetres_flops(net->in_nc, S, H, W) : 0.0;
+}
+extern "C" int qmri_unetres_forward_dev(qmri_net* net, const float* in_dev, float* out_dev, const float* minmax_dev,
+                                        const float* noise_map_dev, int S, int H, int W) {
+    return unetres_forward_dev(net, in_dev, out_dev, minmax_dev, noise_map_dev, S, H, W, 1);
+}
+
+static int net_host_forward(qmri_net* net, const void* in, int in_dtype, void* out, int out_dtype, int S, int H, int W, int orient) {
+    if (!net || !in || !out) return qmri_fail(QMRI_EINVAL, "denoiser: null argument");
+    if (S < 0 || dtype_is_complex(in_dtype) || dtype_is_complex(out_dtype) || !valid_dtype(in_dtype) || !valid_dtype(out_dtype))
+        return qmri_fail(QMRI_EINVAL, "denoiser: arrays must be real single or double");
+    if (S == 0) return QMRI_OK;
+    qmri_ctx* ctx = net->ctx;
+    DevSetter ds(ctx->device);
+    const size_t hw = (size_t)H * W;
+    const size_t nin = hw * net->in_nc * S, nout = hw * 10 * S;
+    const size_t raw = std::max(nin * dtype_size(in_dtype), nout * dtype_size(out_dtype));
+    // io = [planar in | planar out | raw staging]
+    size_t need = (nin + nout) * sizeof(float) + raw + 64;
+    if (need > net->io_elems) {
+        if (net->io) cudaFree(net->io);
+        net->io = nullptr;
+        net->io_elems = 0;
+        cudaError_t e = cudaMalloc((void**)&net->io, need);
+        if (e != cudaSuccess) return qmri_fail(QMRI_ENOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+        net->io_elems = need;
+    }
+    float* d_in = net->io;
+    float* d_out = d_in + nin;
+    void* d_raw = (void*)(d_out + nout + 4);
+    d_raw = (void*)(((uintptr_t)d_raw + 15) & ~(uintptr_t)15);
+    QCUDA(cudaMemcpyAsync(d_raw, in, nin * dtype_size(in_dtype), cudaMemcpyHostToDevice, ctx->stream));
+    QCHECK(unpack_async(ctx, d_raw, in_dtype, d_in, nullptr, nin));
+    // a multi-level (11-channel) host call carries the noise map as its 11th plane: split it off per slice
+    if (net->in_nc == 11) {
+        // planes of slice s: [11][hw]; the kernel wants [S][10][hw] + one shared map -> run slice by slice
+        for (int s = 0; s < S; ++s) {
+            const float* sl = d_in + (size_t)s * 11 * hw;
+            QCHECK(unetres_forward_dev(net, sl, d_out + (size_t)s * 10 * hw, nullptr, sl + 10 * hw, 1, H, W, orient));
+        }
+    } else {
+        QCHECK(unetres_forward_dev(net, d_in, d_out, nullptr, nullptr, S, H, W, orient));
+    }
+    QCHECK(pack_async(ctx, d_raw, out_dtype, d_out, nullptr, nout));
+    QCUDA(cudaMemcpyAsync(out, d_raw, nout * dtype_size(out_dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    QCUDA(cudaStreamSynchronize(ctx->stream));
+    return QMRI_OK;
+}
+extern "C" int qmri_unetres_forward(qmri_net* net, const float* in, float* out, int S, int H, int W) {
+    // PyTorch layout: planes [h][w], w fastest -> internal rows = h (H), fastest extent = W
+    return net_host_forward(net, in, QMRI_F32, out, QMRI_F32, S, H, W, 0);
+}
+extern "C" int qmri_unetres_denoise(qmri_net* net, const void* in, int in_dtype, void* out, int out_dtype, int S, int H, int W) {
+    // MATLAB layout H x W x C: planes [w][h], h fastest -> internal rows = w (W of them), fastest extent = H
+    return net_host_forward(net, in, in_dtype, out, out_dtype, S, W, H, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// ADMM loop
+// ------------------------------------------------------------------------------------------
+struct qmri_admm {
+    qmri_op* op = nullptr;
+    int S = 0;
+    qmri_admm_params prm;
+    DevBuf y, x0_re, x0_im, w_re, w_im, v, x_re, x_im, mm_ord, mm_f, noise, cb_in, cb_out;
+    float *h_in = nullptr, *h_out = nullptr;  // pinned, host-callback path
+    bool uploaded = false;
+};
+
+extern "C" int qmri_admm_create(qmri_op* op, int S, const qmri_admm_params* params, qmri_admm** out) {
+    if (!op || !params || !out) return qmri_fail(QMRI_EINVAL, "qmri_admm_create: null argument");
+    if (S < 1) return qmri_fail(QMRI_EINVAL, "qmri_admm_create: S must be >= 1");
+    if (!(params->gamma > 0.0)) return qmri_fail(QMRI_EINVAL, "param.gamma must be positive");
+    if (params->iters < 0) return qmri_fail(QMRI_EINVAL, "param.iter must be >= 0");
+    if (!params->net && !params->fn) return qmri_fail(QMRI_EINVAL, "param.net missing: pass a qmri_net or a callback");
+    if (params->multi_level && !params->noise_map) return qmri_fail(QMRI_EINVAL, "multi_level denoiser needs param.noise_map");
+    if (params->net && params->net->in_nc != (params->multi_level ? 11 : 10))
+        return qmri_fail(QMRI_EINVAL, "denoiser has %d input channels but denoiser_type wants %d", params->net->in_nc,
+                         params->multi_level ? 11 : 10);
+    if (op->C != 10) return qmri_fail(QMRI_EUNSUPPORTED, "PnP-ADMM needs C == 10 channels (denoiser output), got %d", op->C);
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    qmri_admm* st = new qmri_admm();
+    st->op = op;
+    st->S = S;
+    st->prm = *params;
+    const size_t n = op->plane() * S, hw = (size_t)op->N * op->M;
+    int r = 0;
+    r |= st->y.ensure(std::max<size_t>((size_t)S * op->t.nmeas, 1) * sizeof(float2));
+    r |= st->x0_re.ensure(n * 4); r |= st->x0_im.ensure(n * 4);
+    r |= st->w_re.ensure(n * 4);  r |= st->w_im.ensure(n * 4);
+    r |= st->x_re.ensure(n * 4);  r |= st->x_im.ensure(n * 4);
+    r |= st->v.ensure(n * 4);
+    r |= st->mm_ord.ensure(2 * S * sizeof(int));
+    r |= st->mm_f.ensure(2 * S * sizeof(float));
+    if (params->multi_level) r |= st->noise.ensure(hw * 4);
+    if (!params->net) {
+        const size_t cin = params->multi_level ? 11 : 10;
+        r |= st->cb_in.ensure(hw * cin * S * 4);
+        r |= st->cb_out.ensure(n * 4);
+        if (params->fn_space == QMRI_HOST) {
+            if (cudaMallocHost((void**)&st->h_in, hw * cin * S * 4) != cudaSuccess || cudaMallocHost((void**)&st->h_out, n * 4) != cudaSuccess) r |= 1;
+        }
+    }
+    if (r) {
+        qmri_admm_destroy(st);
+        return qmri_fail(QMRI_ENOMEM, "qmri_admm_create: device allocation failed for S = %d", S);
+    }
+    if (params->multi_level) {
+        cudaError_t e = cudaMemcpy(st->noise.p, params->noise_map, hw * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            qmri_admm_destroy(st);
+            return qmri_fail(QMRI_ECUDA, "noise map upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (params->net) {
+        int rr = unetres_reserve(params->net, S, op->M, op->N);
+        if (rr) {
+            qmri_admm_destroy(st);
+            return rr;
+        }
+    }
+    st->prm.noise_map = nullptr;  // host pointer is not retained
+    *out = st;
+    return QMRI_OK;
+}
+
+extern "C" int qmri_admm_destroy(qmri_admm* st) {
+    if (!st) return QMRI_OK;
+    DevSetter ds(st->op->ctx->device);
+    cudaStreamSynchronize(st->op->ctx->stream);
+    st->y.release(); st->x0_re.release(); st->x0_im.release(); st->w_re.release(); st->w_im.release();
+    st->v.release(); st->x_re.release(); st->x_im.release(); st->mm_ord.release(); st->mm_f.release();
+    st->noise.release(); st->cb_in.release(); st->cb_out.release();
+    if (st->h_in) cudaFreeHost(st->h_in);
+    if (st->h_out) cudaFreeHost(st->h_out);
+    delete st;
+    return QMRI_OK;
+}
+
+extern "C" int qmri_admm_upload(qmri_admm* st, const void* y, int y_dtype, const void* x0, int x0_dtype) {
+    if (!st || !y || !x0) return qmri_fail(QMRI_EINVAL, "qmri_admm_upload: null argument");
+    if (!dtype_is_complex(y_dtype) || !valid_dtype(x0_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_admm_upload: bad dtype");
+    qmri_op* op = st->op;
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    const size_t ny = (size_t)st->S * op->t.nmeas, n = op->plane() * st->S;
+    QCHECK(op->stage.ensure(std::max(ny * dtype_size(y_dtype), n * dtype_size(x0_dtype))));
+    if (ny) {
+        QCUDA(cudaMemcpyAsync(op->stage.p, y, ny * dtype_size(y_dtype), cudaMemcpyHostToDevice, ctx->stream));
+        if (y_dtype == QMRI_C64) cvt_c_in_kernel<float><<<nblk(ny), 256, 0, ctx->stream>>>((const float*)op->stage.p, st->y.as<float2>(), ny);
+        else cvt_c_in_kernel<double><<<nblk(ny), 256, 0, ctx->stream>>>((const double*)op->stage.p, st->y.as<float2>(), ny);
+        QLAUNCH_CHECK(ctx);
+    }
+    QCUDA(cudaMemcpyAsync(op->stage.p, x0, n * dtype_size(x0_dtype), cudaMemcpyHostToDevice, ctx->stream));
+    QCHECK(unpack_async(ctx, op->stage.p, x0_dtype, st->x0_re.as<float>(), st->x0_im.as<float>(), n));
+    st->uploaded = true;
+    return QMRI_OK;
+}
+
+static int admm_k1(qmri_admm* st, bool write_x) {
+    qmri_op* op = st->op;
+    K1Params p = {};
+    k1_fill_tables(op, p);
+    p.mode = K1_ADMM;
+    p.in_re = st->w_re.as<float>();
+    p.in_im = st->w_im.as<float>();
+    p.v = st->v.as<float>();
+    p.out_re = st->w_re.as<float>();  // in place: every cluster reads its whole tile before it writes it
+    p.out_im = st->w_im.as<float>();
+    p.x_re = write_x ? st->x_re.as<float>() : nullptr;
+    p.x_im = write_x ? st->x_im.as<float>() : nullptr;
+    p.y = st->y.as<float2>();
+    p.minmax = st->mm_ord.as<int>();
+    p.inv_1p_rho = (float)(1.0 / (1.0 + st->prm.gamma));
+    return k1_launch(op->ctx, p, st->S, op->t.ns_max, op->k1_mc);
+}
+
+static int admm_denoise(qmri_admm* st) {
+    qmri_op* op = st->op;
+    qmri_ctx* ctx = op->ctx;
+    const int S = st->S;
+    const size_t hw = (size_t)op->N * op->M, n = op->plane() * S;
+    const float* mm = st->mm_f.as<float>();
+    if (st->prm.net) {
+        // planes are MATLAB-ordered: rows = m (M of them), fastest extent = N
+        return unetres_forward_dev(st->prm.net, st->w_re.as<float>(), st->v.as<float>(), mm,
+                                   st->prm.multi_level ? st->noise.as<float>() : nullptr, S, op->M, op->N, 1);
+    }
+    // callback path: v_in = (Re w - min)/range [, noise map]; v = f(v_in) * range + min
+    const int cin = st->prm.multi_level ? 11 : 10;
+    float* vin = st->cb_in.as<float>();
+    if (cin == 10) {
+        QCHECK(normalize_planar(ctx, st->w_re.as<float>(), vin, mm, hw * 10, S, 0));
+    } else {
+        for (int s = 0; s < S; ++s) {
+            QCHECK(normalize_planar(ctx, st->w_re.as<float>() + (size_t)s * hw * 10, vin + (size_t)s * hw * 11, mm + 2 * s, hw * 10, 1, 0));
+            QCUDA(cudaMemcpyAsync(vin + (size_t)s * hw * 11 + hw * 10, st->noise.p, hw * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    int rc;
+    if (st->prm.fn_space == QMRI_DEVICE) {
+        rc = st->prm.fn(st->prm.user, vin, st->cb_out.as<float>(), op->N, op->M, cin, 10, S, QMRI_DEVICE, (void*)ctx->stream);
+    } else {
+        QCUDA(cudaMemcpyAsync(st->h_in, vin, hw * cin * S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        QCUDA(cudaStreamSynchronize(ctx->stream));
+        rc = st->prm.fn(st->prm.user, st->h_in, st->h_out, op->N, op->M, cin, 10, S, QMRI_HOST, nullptr);
+        if (rc == 0) QCUDA(cudaMemcpyAsync(st->cb_out.p, st->h_out, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (rc != 0) return qmri_fail(QMRI_ECALLBACK, "denoiser callback returned %d", rc);
+    return normalize_planar(ctx, st->cb_out.as<float>(), st->v.as<float>(), mm, hw * 10, S, 1);
+}
+
+extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
+    if (!st) return qmri_fail(QMRI_EINVAL, "null state");
+    if (!st->uploaded) return qmri_fail(QMRI_EINVAL, "qmri_admm_run: call qmri_admm_upload first");
+    if (iters < 0) return qmri_fail(QMRI_EINVAL, "iters must be >= 0");
+    qmri_op* op = st->op;
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    const int S = st->S;
+    const size_t n = op->plane() * S;
+    // x = v = X0, uold = 0 (PnP_ADMM.m:76-78): w_1 = x_1 + u_0 = X0 because A X0 = y makes iteration 1's solve a no-op
+    QCUDA(cudaMemcpyAsync(st->w_re.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    QCUDA(cudaMemcpyAsync(st->w_im.p, st->x0_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    QCUDA(cudaMemcpyAsync(st->x_re.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    QCUDA(cudaMemcpyAsync(st->x_im.p, st->x0_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    QCHECK(k1_minmax_init(ctx, st->mm_ord.as<int>(), S));
+    for (int k = 0; k < iters; ++k) {
+        if (k == 0) {
+            dim3 grid(std::min<unsigned>(nblk(op->plane()), 256), S);
+            add_minmax_kernel<<<grid, 256, 0, ctx->stream>>>(st->w_re.as<float>(), st->w_im.as<float>(), nullptr, nullptr, nullptr,
+                                                            nullptr, op->plane(), st->mm_ord.as<int>());
+            QLAUNCH_CHECK(ctx);
+        } else {
+            QCHECK(admm_k1(st, k == iters - 1));
+        }
+        minmax_finalize_kernel<<<nblk(S, 128), 128, 0, ctx->stream>>>(st->mm_ord.as<int>(), st->mm_f.as<float>(), S);
+        QLAUNCH_CHECK(ctx);
+        QCHECK(admm_denoise(st));
+    }
+    return QMRI_OK;
+}
+
+extern "C" int qmri_admm_xupdate_only(qmri_admm* st, int reps) {
+    if (!st || !st->uploaded) return qmri_fail(QMRI_EINVAL, "qmri_admm_xupdate_only: state not ready");
+    DevSetter ds(st->op->ctx->device);
+    for (int i = 0; i < reps; ++i) QCHECK(admm_k1(st, false));
+    return QMRI_OK;
+}
+
+extern "C" int qmri_admm_download(qmri_admm* st, void* x_out, int x_dtype) {
+    if (!st || !x_out) return qmri_fail(QMRI_EINVAL, "qmri_admm_download: null argument");
+    if (!dtype_is_complex(x_dtype)) return qmri_fail(QMRI_EINVAL, "x must be complex");
+    DevSetter ds(st->op->ctx->device);
+    return image_download(st->op, x_out, x_dtype, st->S, st->x_re.as<float>(), st->x_im.as<float>());
+}
+
+extern "C" int qmri_admm_state_dev(qmri_admm* st, const float** x_re, const float** x_im) {
+    if (!st) return qmri_fail(QMRI_EINVAL, "null state");
+    if (x_re) *x_re = st->x_re.as<float>();
+    if (x_im) *x_im = st->x_im.as<float>();
+    return QMRI_OK;
+}
+
+extern "C" int qmri_pnp_admm(qmri_op* op, const void* y, int y_dtype, const void* x0, int x0_dtype, int S,
+                             const qmri_admm_params* params, void* x_out, int x_dtype) {
+    if (!params) return qmri_fail(QMRI_EINVAL, "qmri_pnp_admm: null params");
+    qmri_admm* st = nullptr;
+    QCHECK(qmri_admm_create(op, S, params, &st));
+    int r = qmri_admm_upload(st, y, y_dtype, x0, x0_dtype);
+    if (!r) r = qmri_admm_run(st, params->iters);
+    if (!r) r = qmri_admm_download(st, x_out, x_dtype);
+    qmri_admm_destroy(st);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// dictionary matching
+// ------------------------------------------------------------------------------------------
+struct qmri_dict {
+    qmri_ctx* ctx = nullptr;
+    int64_t K = 0, a0 = 0, a1 = 0;
+    int C = 0, CP = 0, Q = 0;
+    float *Dp = nullptr, *normD = nullptr, *lut = nullptr;
+    DevBuf stage, x_re, x_im, keys, qmap, pd, mt, dm;
+};
+
+extern "C" int qmri_dict_load(qmri_ctx* ctx, const float* D, const float* normD, const float* lut, int64_t K, int C, int Q,
+                              int64_t shard_begin, int64_t shard_end, qmri_dict** out) {
+    if (!ctx || !D || !normD || !lut || !out) return qmri_fail(QMRI_EINVAL, "qmri_dict_load: null argument");
+    if (K < 1 || K >= 0xFFFFFFFFll) return qmri_fail(QMRI_EINVAL, "dictionary size K = %lld out of range", (long long)K);
+    if (C < 1 || C > 16) return qmri_fail(QMRI_EUNSUPPORTED, "dictionary matching supports 1..16 channels (got %d)", C);
+    if (Q < 1) return qmri_fail(QMRI_EINVAL, "lut needs at least one column");
+    if (shard_begin < 0 || shard_end > K || shard_begin >= shard_end) return qmri_fail(QMRI_EINVAL, "bad atom shard [%lld,%lld)", (long long)shard_begin, (long long)shard_end);
+    DevSetter ds(ctx->device);
+    qmri_dict* d = new qmri_dict();
+    d->ctx = ctx;
+    d->K = K; d->C = C; d->Q = Q; d->a0 = shard_begin; d->a1 = shard_end;
+    d->CP = k2_padded_channels(C);
+    std::vector<float> Dp((size_t)K * d->CP, 0.f);
+    for (int c = 0; c < C; ++c)
+        for (int64_t k = 0; k < K; ++k) Dp[(size_t)k * d->CP + c] = D[(size_t)c * K + k];
+    int r = dev_alloc(&d->Dp, Dp.size()) | dev_alloc(&d->normD, (size_t)K) | dev_alloc(&d->lut, (size_t)K * Q);
+    if (r) {
+        qmri_dict_destroy(d);
+        return QMRI_ENOMEM;
+    }
+    cudaMemcpy(d->Dp, Dp.data(), Dp.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d->normD, normD, (size_t)K * 4, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(d->lut, lut, (size_t)K * Q * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        qmri_dict_destroy(d);
+        return qmri_fail(QMRI_ECUDA, "dictionary upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = d;
+    return QMRI_OK;
+}
+extern "C" int qmri_dict_destroy(qmri_dict* d) {
+    if (!d) return QMRI_OK;
+    DevSetter ds(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    cudaFree(d->Dp); cudaFree(d->normD); cudaFree(d->lut);
+    d->stage.release(); d->x_re.release(); d->x_im.release(); d->keys.release();
+    d->qmap.release(); d->pd.release(); d->mt.release(); d->dm.release();
+    delete d;
+    return QMRI_OK;
+}
+
+extern "C" int qmri_match_keys_dev(qmri_dict* d, const float* x_re, const float* x_im, int64_t npix, uint64_t* keys_dev) {
+    if (!d || !x_re || !keys_dev) return qmri_fail(QMRI_EINVAL, "qmri_match_keys_dev: null argument");
+    if (npix < 0) return qmri_fail(QMRI_EINVAL, "npix < 0");
+    if (npix == 0) return QMRI_OK;
+    DevSetter ds(d->ctx->device);
+    QCUDA(cudaMemsetAsync(keys_dev, 0, (size_t)npix * 8, d->ctx->stream));
+    K2Params p = {};
+    p.x_re = x_re; p.x_im = x_im; p.npix = npix; p.Dp = d->Dp; p.a0 = d->a0; p.a1 = d->a1;
+    p.keys = (unsigned long long*)keys_dev; p.C = d->C; p.CP = d->CP;
+    return k2_launch_keys(d->ctx, p);
+}
+extern "C" int qmri_match_finish_dev(qmri_dict* d, const float* x_re, const float* x_im, int64_t npix, const uint64_t* keys_dev,
+                                     float* qmap_dev, float* pd_dev, float* mt_dev, int32_t* dm_dev) {
+    if (!d || !x_re || !keys_dev) return qmri_fail(QMRI_EINVAL, "qmri_match_finish_dev: null argument");
+    if (npix <= 0) return npix == 0 ? QMRI_OK : qmri_fail(QMRI_EINVAL, "npix < 0");
+    DevSetter ds(d->ctx->device);
+    K2Finish f = {};
+    f.x_re = x_re; f.x_im = x_im; f.npix = npix; f.Dp = d->Dp; f.normD = d->normD; f.lut = d->lut;
+    f.K = d->K; f.C = d->C; f.CP = d->CP; f.Q = d->Q; f.keys = (const unsigned long long*)keys_dev;
+    f.qmap = qmap_dev; f.pd = pd_dev; f.mt = mt_dev; f.dm = dm_dev;
+    return k2_launch_finish(d->ctx, f);
+}
+extern "C" int qmri_match_dev(qmri_dict* d, const float* x_re, const float* x_im, int64_t npix, float* qmap_dev, float* pd_dev,
+                              float* mt_dev, int32_t* dm_dev) {
+    if (!d) return qmri_fail(QMRI_EINVAL, "null dict");
+    if (npix <= 0) return npix == 0 ? QMRI_OK : qmri_fail(QMRI_EINVAL, "npix < 0");
+    DevSetter ds(d->ctx->device);
+    QCHECK(d->keys.ensure((size_t)npix * 8));
+    QCHECK(qmri_match_keys_dev(d, x_re, x_im, npix, d->keys.as<uint64_t>()));
+    return qmri_match_finish_dev(d, x_re, x_im, npix, d->keys.as<uint64_t>(), qmap_dev, pd_dev, mt_dev, dm_dev);
+}
+extern "C" int qmri_match(qmri_dict* d, const void* x, int x_dtype, int64_t npix, float* qmap, float* pd, float* mt, int32_t* dm) {
+    if (!d || (!x && npix > 0)) return qmri_fail(QMRI_EINVAL, "qmri_match: null argument");
+    if (npix < 0 || !valid_dtype(x_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_match: bad npix / dtype");
+    if (npix == 0) return QMRI_OK;
+    if (d->a0 != 0 || d->a1 != d->K)
+        return qmri_fail(QMRI_EINVAL, "qmri_match on an atom-sharded handle: use qmri_match_keys_dev + a max-reduction + qmri_match_finish_dev");
+    qmri_ctx* ctx = d->ctx;
+    DevSetter ds(ctx->device);
+    const size_t n = (size_t)npix * d->C;
+    const int cplx = dtype_is_complex(x_dtype);
+    QCHECK(d->stage.ensure(n * dtype_size(x_dtype)));
+    QCHECK(d->x_re.ensure(n * 4));
+    if (cplx) QCHECK(d->x_im.ensure(n * 4));
+    QCUDA(cudaMemcpyAsync(d->stage.p, x, n * dtype_size(x_dtype), cudaMemcpyHostToDevice, ctx->stream));
+    QCHECK(unpack_async(ctx, d->stage.p, x_dtype, d->x_re.as<float>(), cplx ? d->x_im.as<float>() : nullptr, n));
+    if (qmap) QCHECK(d->qmap.ensure((size_t)npix * d->Q * 4));
+    if (pd) QCHECK(d->pd.ensure((size_t)npix * 8));
+    if (mt) QCHECK(d->mt.ensure((size_t)npix * 4));
+    if (dm) QCHECK(d->dm.ensure((size_t)npix * 4));
+    QCHECK(qmri_match_dev(d, d->x_re.as<float>(), cplx ? d->x_im.as<float>() : nullptr, npix, qmap ? d->qmap.as<float>() : nullptr,
+                          pd ? d->pd.as<float>() : nullptr, mt ? d->mt.as<float>() : nullptr, dm ? d->dm.as<int32_t>() : nullptr));
+    if (qmap) QCUDA(cudaMemcpyAsync(qmap, d->qmap.p, (size_t)npix * d->Q * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pd) QCUDA(cudaMemcpyAsync(pd, d->pd.p, (size_t)npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mt) QCUDA(cudaMemcpyAsync(mt, d->mt.p, (size_t)npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dm) QCUDA(cudaMemcpyAsync(dm, d->dm.p, (size_t)npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    QCUDA(cudaStreamSynchronize(ctx->stream));
+    return QMRI_OK;
+}
+
+extern "C" int qmri_synthesize(qmri_dict* d, const float* qmap, int64_t npix, float* X, int32_t* atom_index) {
+    (void)d; (void)qmap; (void)npix; (void)X; (void)atom_index;
+    return qmri_fail(QMRI_EUNSUPPORTED, "qmri_synthesize (SURVEY.md 8f-1, main_synthesize_tsmis.m:84-98) is not built yet");
+}

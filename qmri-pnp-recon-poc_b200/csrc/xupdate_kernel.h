@@ -1,0 +1,36 @@
+// Host-visible interface of the K1 kernel (see xupdate_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct qmri_ctx;
+
+enum { K1_ADMM = 0, K1_SOLVE = 1, K1_FORWARD = 2, K1_ADJOINT = 3 };
+
+struct K1Params {
+    // planar fp32 images [S][C][M][N] (n fastest - the MATLAB layout of an N x M x C x S array)
+    const float* in_re;   // ADMM: Re w       SOLVE/FORWARD: Re z
+    const float* in_im;   // ADMM: Im w       SOLVE/FORWARD: Im z (may be null = real input)
+    const float* v;       // ADMM: denoised v (real)
+    float* out_re;        // ADMM: Re w'      SOLVE: Re x      ADJOINT: Re A^H y
+    float* out_im;
+    float* x_re;          // ADMM only, optional: x of this iteration (written on the last one)
+    float* x_im;
+    const float2* y;      // [S][nmeas] measurements
+    float2* y_out;        // FORWARD: [S][nmeas]
+    int* minmax;          // optional [S][2] ordered-int min / max of out_re
+    // per-operator tables (device)
+    const float2* tw;        // [224] e^{-2 pi i t / 224}
+    const int* frame_ptr;    // [C+1]
+    const uint16_t* samp;    // [nmeas] k1 | k2 << 8, frame-major, ascending k = k1 + 224 k2
+    const uint16_t* row_ptr; // [C][225] CSR over k1 rows of each frame
+    const uint32_t* rowtab;  // [nmeas] per frame, row-sorted: k2 | (j << 8)
+    const int* row_grp;      // [C][8] row ranges balancing the sparse inverse pass over 7 warp groups
+    int C;
+    int nmeas;
+    int mode;
+    float inv_1p_rho;
+};
+
+int k1_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max, int mc);
+int k1_minmax_init(qmri_ctx* ctx, int* minmax, int S);

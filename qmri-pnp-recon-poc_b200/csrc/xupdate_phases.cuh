@@ -1,0 +1,210 @@
+// K1 - fused x-update: per-thread phase functions.
+//
+// One thread-block cluster owns one (slice, channel) 224 x 224 image; each CTA of
+// the cluster owns a slab of MC consecutive columns m (MATLAB dim 2) kept in shared
+// memory as interleaved complex fp32.  The data-consistency solve of
+//   PnP_ADMM.m:102 (lsqr over afun :153-171) with F from main_recon_tsmis_FFT.m:228-229
+// is evaluated in its exact closed form for A A^H = I (V = eye):
+//   x = z + A^H (y - A z) / (1 + rho)
+// A z is needed only at the <= ~700 sampled k-space locations of the channel and
+// A^H c is the inverse transform of a sparse array, so the m-direction transforms
+// are evaluated as sparse DFT sums, and only the n-direction (contiguous dim) uses
+// full length-224 FFTs (224 = 14 x 16, two register-resident stages).
+//
+// The functions here are __host__ __device__ so that tests/test_k1_emulation.py can
+// run the exact kernel arithmetic on the CPU (no GPU in the build container).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QHD __host__ __device__ __forceinline__
+#include <cuda_runtime.h>
+#else
+#define QHD inline
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+#endif
+
+namespace k1 {
+
+constexpr int NF = 224;   // image side (N == M == 224) and FFT length
+constexpr int CS = 225;   // shared-memory column stride in float2 (odd: conflict-free across columns)
+constexpr int NROWGRP = 7;
+
+QHD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+QHD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+QHD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+QHD float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+// multiply by -i
+QHD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// position of element (k1, n2) of the 14 x 16 intermediate inside a column; XOR swizzle keeps
+// both the stage-1 stores (lanes = n2) and the stage-2 loads (lanes = k1) bank-conflict free
+QHD int swz(int k1, int n2) { return 16 * k1 + (n2 ^ (k1 & 15)); }
+
+// ---- 7-point DFT (forward, e^{-2 pi i/7}) ----------------------------------------
+QHD void dft7(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4, float2& x5, float2& x6) {
+    const float C1 = 0.62348980185873353f, C2 = -0.22252093395631440f, C3 = -0.90096886790241913f;
+    const float S1 = 0.78183148246802981f, S2 = 0.97492791218182361f, S3 = 0.43388373911755812f;
+    float2 p1 = cadd(x1, x6), p2 = cadd(x2, x5), p3 = cadd(x3, x4);
+    float2 q1 = csub(x1, x6), q2 = csub(x2, x5), q3 = csub(x3, x4);
+    float2 a1 = make_float2(x0.x + C1 * p1.x + C2 * p2.x + C3 * p3.x, x0.y + C1 * p1.y + C2 * p2.y + C3 * p3.y);
+    float2 a2 = make_float2(x0.x + C2 * p1.x + C3 * p2.x + C1 * p3.x, x0.y + C2 * p1.y + C3 * p2.y + C1 * p3.y);
+    float2 a3 = make_float2(x0.x + C3 * p1.x + C1 * p2.x + C2 * p3.x, x0.y + C3 * p1.y + C1 * p2.y + C2 * p3.y);
+    float2 b1 = make_float2(S1 * q1.x + S2 * q2.x + S3 * q3.x, S1 * q1.y + S2 * q2.y + S3 * q3.y);
+    float2 b2 = make_float2(S2 * q1.x - S3 * q2.x - S1 * q3.x, S2 * q1.y - S3 * q2.y - S1 * q3.y);
+    float2 b3 = make_float2(S3 * q1.x - S1 * q2.x + S2 * q3.x, S3 * q1.y - S1 * q2.y + S2 * q3.y);
+    x0 = make_float2(x0.x + p1.x + p2.x + p3.x, x0.y + p1.y + p2.y + p3.y);
+    // X_k = A_k - i B_k ; X_{7-k} = A_k + i B_k
+    x1 = make_float2(a1.x + b1.y, a1.y - b1.x);
+    x6 = make_float2(a1.x - b1.y, a1.y + b1.x);
+    x2 = make_float2(a2.x + b2.y, a2.y - b2.x);
+    x5 = make_float2(a2.x - b2.y, a2.y + b2.x);
+    x3 = make_float2(a3.x + b3.y, a3.y - b3.x);
+    x4 = make_float2(a3.x - b3.y, a3.y + b3.x);
+}
+
+// e^{-2 pi i k / 14}, k = 0..6
+QHD float2 w14(int k) {
+    switch (k) {
+        case 0: return make_float2(1.0f, 0.0f);
+        case 1: return make_float2(0.90096886790241913f, -0.43388373911755812f);
+        case 2: return make_float2(0.62348980185873353f, -0.78183148246802981f);
+        case 3: return make_float2(0.22252093395631440f, -0.97492791218182361f);
+        case 4: return make_float2(-0.22252093395631440f, -0.97492791218182361f);
+        case 5: return make_float2(-0.62348980185873353f, -0.78183148246802981f);
+        default: return make_float2(-0.90096886790241913f, -0.43388373911755812f);
+    }
+}
+
+// 14-point DFT, natural order in and out (radix-2 DIT over two 7-point DFTs)
+QHD void dft14(float2 (&x)[16]) {
+    float2 e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6], e4 = x[8], e5 = x[10], e6 = x[12];
+    float2 o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7], o4 = x[9], o5 = x[11], o6 = x[13];
+    dft7(e0, e1, e2, e3, e4, e5, e6);
+    dft7(o0, o1, o2, o3, o4, o5, o6);
+    float2 t;
+    x[0] = cadd(e0, o0); x[7] = csub(e0, o0);
+    t = cmul(o1, w14(1)); x[1] = cadd(e1, t); x[8] = csub(e1, t);
+    t = cmul(o2, w14(2)); x[2] = cadd(e2, t); x[9] = csub(e2, t);
+    t = cmul(o3, w14(3)); x[3] = cadd(e3, t); x[10] = csub(e3, t);
+    t = cmul(o4, w14(4)); x[4] = cadd(e4, t); x[11] = csub(e4, t);
+    t = cmul(o5, w14(5)); x[5] = cadd(e5, t); x[12] = csub(e5, t);
+    t = cmul(o6, w14(6)); x[6] = cadd(e6, t); x[13] = csub(e6, t);
+}
+
+QHD void dft4(float2& a, float2& b, float2& c, float2& d) {
+    float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = mul_mi(csub(b, d));
+    a = cadd(s0, s2);
+    c = csub(s0, s2);
+    b = cadd(s1, s3);
+    d = csub(s1, s3);
+}
+
+// e^{-2 pi i k / 16}, k = 0..9 (all that 4x4 needs)
+QHD float2 w16(int k) {
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+    switch (k) {
+        case 0: return make_float2(1.0f, 0.0f);
+        case 1: return make_float2(c1, -s1);
+        case 2: return make_float2(r, -r);
+        case 3: return make_float2(s1, -c1);
+        case 4: return make_float2(0.0f, -1.0f);
+        case 6: return make_float2(-r, -r);
+        default: return make_float2(-c1, s1);  // k == 9
+    }
+}
+
+// 16-point DFT, natural order in and out: n = 4a + b, k = ka + 4 kb
+QHD void dft16(float2 (&x)[16]) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dft4(x[b], x[4 + b], x[8 + b], x[12 + b]);  // over a; result index ka at x[4 ka + b]
+#pragma unroll
+    for (int ka = 1; ka < 4; ++ka)
+#pragma unroll
+        for (int b = 1; b < 4; ++b) x[4 * ka + b] = cmul(x[4 * ka + b], w16(ka * b));
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) dft4(x[4 * ka + 0], x[4 * ka + 1], x[4 * ka + 2], x[4 * ka + 3]);  // over b; kb at x[4 ka + kb]
+    // x[4 ka + kb] holds X[ka + 4 kb] -> transpose to natural order
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka)
+#pragma unroll
+        for (int kb = ka + 1; kb < 4; ++kb) {
+            float2 t = x[4 * ka + kb];
+            x[4 * ka + kb] = x[4 * kb + ka];
+            x[4 * kb + ka] = t;
+        }
+}
+
+// ---- length-224 FFT along a shared-memory column, 16 threads per column -----------
+// X[k1 + 14 k2] = sum_{n2} w16^{n2 k2} [ w224^{n2 k1} sum_{n1} x[16 n1 + n2] w14^{n1 k1} ]
+// The inverse transform is the forward one with re/im swapped on the way in and out.
+template <bool INV>
+QHD void fft_s1_load(const float2* col, int n2, const float2* tw, float2 (&a)[16]) {
+#pragma unroll
+    for (int n1 = 0; n1 < 14; ++n1) {
+        float2 v = col[16 * n1 + n2];
+        a[n1] = INV ? cswap(v) : v;
+    }
+    dft14(a);
+#pragma unroll
+    for (int k1 = 1; k1 < 14; ++k1) a[k1] = cmul(a[k1], tw[n2 * k1]);
+}
+QHD void fft_s1_store(float2* col, int n2, const float2 (&a)[16]) {
+#pragma unroll
+    for (int k1 = 0; k1 < 14; ++k1) col[swz(k1, n2)] = a[k1];
+}
+QHD void fft_s2_load(const float2* col, int k1, float2 (&b)[16]) {
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) b[n2] = col[swz(k1, n2)];
+    dft16(b);
+}
+template <bool INV>
+QHD void fft_s2_store(float2* col, int k1, const float2 (&b)[16]) {
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) col[k1 + 14 * k2] = INV ? cswap(b[k2]) : b[k2];
+}
+
+// ---- sparse m-direction transforms -------------------------------------------------
+// forward: partial sum over this CTA's columns of  T[m][k1] * e^{-2 pi i k2 m / 224}
+template <int MC>
+QHD float2 sampled_dft_partial(const float2* cols, const float2* tw, int m0, int k1, int k2) {
+    int idx = (k2 * m0) % NF;
+    float ax = 0.f, ay = 0.f;
+#pragma unroll 4
+    for (int mm = 0; mm < MC; ++mm) {
+        float2 t = tw[idx];
+        float2 v = cols[mm * CS + k1];
+        ax = fmaf(v.x, t.x, ax);
+        ax = fmaf(-v.y, t.y, ax);
+        ay = fmaf(v.x, t.y, ay);
+        ay = fmaf(v.y, t.x, ay);
+        idx += k2;
+        if (idx >= NF) idx -= NF;
+    }
+    return make_float2(ax, ay);
+}
+
+// inverse: column m of the sparse k-space array, rows [r0, r1): T'[m][k1] = sum_j c_j e^{+2 pi i k2_j m / 224}
+// row_ptr: CSR over k1 for this frame (225 entries), rowtab[e] = k2 | (j << 8)
+QHD void sparse_idft_rows(float2* col, const float2* c, const float2* tw, const uint16_t* row_ptr,
+                          const uint32_t* rowtab, int m, int r0, int r1) {
+    for (int k1 = r0; k1 < r1; ++k1) {
+        int e0 = row_ptr[k1], e1 = row_ptr[k1 + 1];
+        float ax = 0.f, ay = 0.f;
+        for (int e = e0; e < e1; ++e) {
+            uint32_t ent = rowtab[e];
+            int k2 = ent & 0xff;
+            float2 cj = c[ent >> 8];
+            float2 t = tw[(k2 * m) % NF];  // conj(t) = e^{+...}
+            ax = fmaf(cj.x, t.x, ax);
+            ax = fmaf(cj.y, t.y, ax);
+            ay = fmaf(cj.y, t.x, ay);
+            ay = fmaf(-cj.x, t.y, ay);
+        }
+        col[k1] = make_float2(ax, ay);
+    }
+}
+
+}  // namespace k1

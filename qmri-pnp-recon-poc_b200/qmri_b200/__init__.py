@@ -1,0 +1,21 @@
+"""qmri_b200 - host-side mirror of the reference's MATLAB operator surface over libqmri_b200.so.
+
+Same names, argument meaning and error behaviour as ketanfatania/QMRI-PnP-Recon-POC for the
+PnP-ADMM MRF reconstruction hot path; all arithmetic runs in hand-written sm_100a CUDA kernels
+behind the C ABI of include/qmri.h.  There is no CPU fallback: a missing library or a missing
+B200 raises.
+"""
+from ._capi import (QMRI_C128, QMRI_C64, QMRI_DEVICE, QMRI_F32, QMRI_F64, QMRI_HOST, Context, QmriError,
+                    load_library)
+from .admm import AdmmSession, PnP_ADMM
+from .denoiser import UNetRes, build_noise_map, denoiseImage_PnP_ADMM, state_dict_keys
+from .matching import Dictionary, mrf_dtm, mrf_dtm_cpu
+from .operators import (FOperator, SubsamplingPattern, fft_operator, setup_subsampling_epi,
+                        setup_subsampling_explicit, setup_subsampling_spiralgrided)
+
+__all__ = [
+    "Context", "QmriError", "load_library", "PnP_ADMM", "AdmmSession", "UNetRes", "build_noise_map",
+    "denoiseImage_PnP_ADMM", "state_dict_keys", "Dictionary", "mrf_dtm", "mrf_dtm_cpu", "FOperator",
+    "SubsamplingPattern", "fft_operator", "setup_subsampling_epi", "setup_subsampling_explicit",
+    "setup_subsampling_spiralgrided", "QMRI_F32", "QMRI_F64", "QMRI_C64", "QMRI_C128", "QMRI_HOST", "QMRI_DEVICE",
+]

@@ -1,0 +1,356 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star):
+  * operator / x-update : relative L2 <= 1e-5 vs the float64 oracle
+  * matching            : atom indices identical except oracle near-ties (top-2 relative gap < 1e-6)
+  * denoiser            : relative L2 <= 1e-4 vs the fp32 CPU forward with the same weights
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_XUPDATE = 1e-5
+TOL_DENOISER = 1e-4
+NEAR_TIE = 1e-6
+
+
+@pytest.fixture(scope="module")
+def q():
+    import qmri_b200
+    qmri_b200.Context.default()  # raises without a B200: no fallback
+    return qmri_b200
+
+
+@pytest.fixture(scope="module")
+def ops(q):
+    from oracle import sampling
+    V = np.eye(10)
+    out = {}
+    out["spiral"] = (q.setup_subsampling_spiralgrided(224, 224, 771, V), sampling.setup_subsampling_spiralgrided(224, 224, 771, V))
+    out["epi"] = (q.setup_subsampling_epi(224, 224, 1 / 65, V), sampling.setup_subsampling_epi(224, 224, 1 / 65, V))
+    return out
+
+
+def smooth_tsmi(seed, S=None, cplx=False):
+    """Smooth, brain-like-ish random TSMI (N x M x C [x S])."""
+    rng = np.random.default_rng(seed)
+    shape = (224, 224, 10) + (() if S is None else (S,))
+    n = np.arange(224)[:, None, None] / 224.0
+    m = np.arange(224)[None, :, None] / 224.0
+    c = np.arange(10)[None, None, :]
+    base = np.exp(-((n - 0.5) ** 2 + (m - 0.45) ** 2) * 8) * np.cos(0.3 * c) + 0.2 * np.sin(7 * n + c) * np.cos(5 * m)
+    x = base if S is None else np.repeat(base[..., None], S, axis=3)
+    x = x + 0.05 * rng.standard_normal(shape)
+    if cplx:
+        x = x + 1j * (0.3 * np.roll(x, 5, axis=0) + 0.05 * rng.standard_normal(shape))
+    return x
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["spiral", "epi"])
+def test_mask_constructors_match_oracle(ops, name):
+    P, Po = ops[name]
+    idx, fp = P.indices()
+    assert P.nmeas == Po.nmeas
+    assert np.array_equal(fp, Po.frame_ptr)
+    assert np.array_equal(idx, Po.idx)
+
+
+@pytest.mark.parametrize("name", ["spiral", "epi"])
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32, np.complex64])
+def test_forward_adjoint(q, ops, name, dtype):
+    from oracle.sampling import FOperator
+    P, Po = ops[name]
+    F, Fo = q.fft_operator(P), FOperator(Po)
+    x = smooth_tsmi(1, cplx=np.issubdtype(dtype, np.complexfloating)).astype(dtype)
+    y = F.forward(x)
+    yo = Fo.forward(x.astype(np.complex128))
+    assert y.shape == yo.shape
+    assert rel_l2(y, yo) <= TOL_XUPDATE
+    xa = F.adjoint(yo)
+    xo = Fo.adjoint(yo)
+    assert rel_l2(xa, xo) <= TOL_XUPDATE
+
+
+def test_forward_adjoint_batched_and_adjointness(q, ops):
+    from oracle.sampling import FOperator
+    P, Po = ops["spiral"]
+    F, Fo = q.fft_operator(P), FOperator(Po)
+    x = smooth_tsmi(2, S=3, cplx=True)
+    y = F.forward(x)
+    assert y.shape == (P.nmeas, 3)
+    for s in range(3):
+        assert rel_l2(y[:, s], Fo.forward(x[..., s])) <= TOL_XUPDATE
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal((P.nmeas, 3)) + 1j * rng.standard_normal((P.nmeas, 3))
+    xa = F.adjoint(b)
+    # <A x, b> == <x, A^H b>, and A A^H = I when V = eye
+    lhs, rhs = np.vdot(b, y), np.vdot(xa, x)
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    assert rel_l2(F.forward(xa), b) <= TOL_XUPDATE
+
+
+@pytest.mark.parametrize("name", ["spiral", "epi"])
+def test_xupdate_matches_exact_solve(q, ops, name):
+    from oracle.sampling import FOperator
+    from oracle.xupdate import xupdate_exact
+    P, Po = ops[name]
+    F, Fo = q.fft_operator(P), FOperator(Po)
+    x_true = smooth_tsmi(3)
+    y = Fo.forward(x_true)
+    v = smooth_tsmi(4)
+    u = 0.1 * smooth_tsmi(5, cplx=True)
+    rho = 0.05
+    x, w, mm = F.xupdate(y, v, u, rho, want_w=True)
+    xo = xupdate_exact(Fo, y, v - u, rho)
+    assert rel_l2(x, xo) <= TOL_XUPDATE
+    wo = xo + u
+    assert rel_l2(w, wo) <= TOL_XUPDATE
+    assert abs(mm[0] - wo.real.min()) <= 1e-5 * abs(wo.real).max()
+    assert abs(mm[1] - wo.real.max()) <= 1e-5 * abs(wo.real).max()
+    # u omitted = the scalar 0 of PnP_ADMM.m:78
+    x2 = F.xupdate(y, v, None, rho)
+    assert rel_l2(x2, xupdate_exact(Fo, y, v, rho)) <= TOL_XUPDATE
+
+
+def test_xupdate_appendix_a2_known_answers(q, ops):
+    """SURVEY.md Appendix A.2 (independent float64 restatement): deterministic inputs."""
+    n = np.arange(1, 225)[:, None, None]
+    m = np.arange(1, 225)[None, :, None]
+    c = np.arange(1, 11)[None, None, :]
+    X0 = np.sin(0.1 * n + 0.05 * c) * np.cos(0.07 * m) + 0.01 * c
+    z = 0.9 * X0 + 0.1j * np.roll(X0, 3, axis=0)
+    expect = {"spiral": (3.124627321012e+04, 1.089099617982e+05, 6.803444208467e-01 + 2.255400393693e-02j),
+              "epi": (6.178596834661e+03, 1.041382994863e+05, 6.691885559181e-01 + 6.113009617138e-02j)}
+    for name, (ynorm2, xnorm2, x100_50_5) in expect.items():
+        F = q.fft_operator(ops[name][0])
+        y = F.forward(X0)
+        assert abs((np.abs(y) ** 2).sum() - ynorm2) <= 2e-5 * ynorm2
+        x = F.xupdate(y, z, None, 0.05)
+        assert abs((np.abs(x) ** 2).sum() - xnorm2) <= 2e-5 * xnorm2
+        assert abs(x[99, 49, 4] - x100_50_5) <= 1e-5 * abs(x100_50_5) * 10
+
+
+# ---------------------------------------------------------------------------------------------
+def a3_dictionary():
+    K = 1000
+    k = np.arange(1, K + 1)[:, None]
+    cc = np.arange(1, 11)[None, :]
+    Draw = np.cos(0.37 * k * cc + 0.11 * cc ** 2) + 0.5 * np.sin(0.013 * k + cc)
+    normD = np.linalg.norm(Draw, axis=1)
+    lut = np.stack([0.1 + 3.9 * (k[:, 0] - 1) / (K - 1), 0.01 + 0.59 * np.mod(7 * (k[:, 0] - 1), K) / (K - 1)], 1)
+    return {"D": Draw / normD[:, None], "normD": normD, "lut": lut}
+
+
+def check_match(out, ref, K):
+    dm = out["dm"].reshape(-1, order="F").astype(np.int64)
+    dmo = ref["dm"].reshape(-1, order="F")
+    gap = ref["gap"].reshape(-1, order="F")
+    decided = gap >= NEAR_TIE
+    assert np.array_equal(dm[decided], dmo[decided]), f"{(dm[decided] != dmo[decided]).sum()} index mismatches outside near-ties"
+    assert dm.min() >= 1 and dm.max() <= K
+    same = dm == dmo
+    q_, qo = out["qmap"].reshape(-1, out["qmap"].shape[-1], order="F"), ref["qmap"].reshape(-1, ref["qmap"].shape[-1], order="F")
+    assert np.array_equal(q_[same], qo[same])
+    pd, pdo = out["pd"].reshape(-1, order="F"), ref["pd"].reshape(-1, order="F")
+    assert rel_l2(pd[same], pdo[same]) <= 1e-5
+    return int((~same).sum())
+
+
+def test_match_appendix_a3(q):
+    """K = 1000 analytic dictionary, complex data, 22 near-tie pixels."""
+    from oracle.matching import mrf_dtm_cpu as oracle_match
+    n = np.arange(1, 225)[:, None, None]
+    m = np.arange(1, 225)[None, :, None]
+    c = np.arange(1, 11)[None, None, :]
+    X0 = np.sin(0.1 * n + 0.05 * c) * np.cos(0.07 * m) + 0.01 * c
+    z = 0.9 * X0 + 0.1j * np.roll(X0, 3, axis=0)
+    d = a3_dictionary()
+    par = {"f": {"qout": 1, "pdout": 1, "mtout": 1, "dmout": 1, "Xout": 0, "Yout": 0, "verbose": 0}, "fp": {"blockSize": 1e9}}
+    out = q.mrf_dtm_cpu(d, {"X": z}, par)
+    ref = oracle_match(d, {"X": z}, par, return_gap=True)
+    assert out["qmap"].shape == (224, 224, 2) and out["pd"].shape == (224, 224)
+    assert out["pd"].dtype == np.complex64 and out["qmap"].dtype == np.float32
+    nmis = check_match(out, ref, 1000)
+    assert nmis <= 22
+    assert rel_l2(out["mt"], ref["mt"]) <= 1e-5
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_match_synthetic_dictionary(q, cplx):
+    from oracle import synth
+    from oracle.matching import mrf_dtm_cpu as oracle_match
+    d = synth.make_dictionary(K_target=6000, cut=3, seed=1)
+    K = d["D"].shape[0]
+    rng = np.random.default_rng(7)
+    # pixels = scaled noisy atoms (realistic: near-collinear neighbours compete) + a zero pixel + ragged count
+    pick = rng.integers(0, K, size=3001)
+    X = d["D"][pick].astype(np.float64) * rng.uniform(0.2, 2.0, size=(3001, 1)) + 0.01 * rng.standard_normal((3001, 10))
+    if cplx:
+        X = X * np.exp(1j * rng.uniform(0, 2 * np.pi, size=(3001, 1)))
+    X[17] = 0
+    X = X.reshape(3001, 1, 10)
+    par = {"f": {"qout": 1, "pdout": 1, "mtout": 0, "dmout": 1}}
+    out = q.mrf_dtm_cpu(d, {"X": X}, par)
+    ref = oracle_match(d, {"X": X}, par, return_gap=True)
+    check_match(out, ref, K)
+    assert out["dm"].reshape(-1)[17] == 1  # all-zero pixel: MATLAB max returns the first index
+
+
+def test_match_lut_nan_becomes_zero_and_first_index_ties(q):
+    rng = np.random.default_rng(3)
+    D = rng.standard_normal((64, 10))
+    D[40] = D[5]      # exact duplicate atoms: the lower index must win
+    D /= np.linalg.norm(D, axis=1, keepdims=True)
+    lut = np.stack([np.arange(64, dtype=np.float64), np.arange(64, dtype=np.float64) * 2], 1)
+    lut[5, 1] = np.nan
+    d = {"D": D, "normD": np.ones(64), "lut": lut}
+    X = (3.0 * D[5])[None, None, :]
+    out = q.mrf_dtm_cpu(d, {"X": X}, {"f": {"qout": 1, "pdout": 1, "dmout": 1}})
+    assert out["dm"][0, 0] == 6
+    assert out["qmap"][0, 0, 0] == 5.0 and out["qmap"][0, 0, 1] == 0.0
+    assert abs(out["pd"][0, 0] - 3.0) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def nets(q):
+    from oracle import unetres
+    sd = unetres.make_state_dict(10, seed=0)
+    return q.UNetRes(sd, in_nc=10), sd
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 64, 40)])
+def test_denoiser_matches_cpu_forward(q, nets, shape):
+    import torch
+    from oracle import unetres
+    net, sd = nets
+    S, H, W = shape
+    torch.manual_seed(11)
+    x = torch.rand(S, 10, H, W)
+    with torch.no_grad():
+        ref = unetres.unetres_forward(sd, x).numpy()
+    out = net.forward(x.numpy())
+    assert out.shape == ref.shape
+    assert rel_l2(out, ref) <= TOL_DENOISER
+
+
+def test_denoiser_matlab_layout_and_wrapper(q, nets):
+    from oracle import unetres
+    net, sd = nets
+    rng = np.random.default_rng(5)
+    A = rng.random((48, 32, 10))           # H x W x C, double like MATLAB
+    ref = unetres.denoise_matlab_layout(sd, A)
+    out = q.denoiseImage_PnP_ADMM(A, net, True, False)
+    assert out.dtype == np.float64 and out.shape == (48, 32, 10)
+    assert rel_l2(out, ref) <= TOL_DENOISER
+    res = q.denoiseImage_PnP_ADMM(A, net, True, True)
+    assert rel_l2(res, A - ref) <= 1e-4
+    assert q.denoiseImage_PnP_ADMM(A, net, "yes", False) is None  # the reference's soft failure
+
+
+def test_denoiser_multi_level_11_channels(q):
+    import torch
+    from oracle import unetres
+    sd = unetres.make_state_dict(11, seed=0)
+    net = q.UNetRes(sd, in_nc=11)
+    torch.manual_seed(3)
+    x = torch.rand(1, 11, 32, 32)
+    x[:, 10] = 0.01
+    with torch.no_grad():
+        ref = unetres.unetres_forward(sd, x).numpy()
+    assert rel_l2(net.forward(x.numpy()), ref) <= TOL_DENOISER
+
+
+# ---------------------------------------------------------------------------------------------
+def box_denoiser(v):
+    """A cheap deterministic stand-in for param.net: 5-point average on the first 10 channels."""
+    v = np.asarray(v, dtype=np.float64)[:, :, :10]
+    return (v + np.roll(v, 1, 0) + np.roll(v, -1, 0) + np.roll(v, 1, 1) + np.roll(v, -1, 1)) / 5.0
+
+
+def make_problem(Po, seed, S=None):
+    from oracle.sampling import FOperator
+    from oracle.synth import awgn_measured
+    Fo = FOperator(Po)
+    Xgt = smooth_tsmi(seed, S=S)
+    Y = awgn_measured(Fo.forward(Xgt), 30, seed)
+    return Fo, Xgt, Y, Fo.adjoint(Y)
+
+
+@pytest.mark.parametrize("name", ["spiral", "epi"])
+def test_admm_loop_with_callback_denoiser(q, ops, name):
+    from oracle.admm import pnp_admm
+    P, Po = ops[name]
+    Fo, Xgt, Y, X0 = make_problem(Po, 21)
+    param = {"iter": 6, "gamma": 0.05, "cg_tol": 1e-4, "gt_tsmi": Xgt, "X0": X0, "denoiser_type": "single_level"}
+    xo = pnp_admm(Y, dict(param, F=Fo, net=box_denoiser), solver="exact")
+    x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=box_denoiser))
+    assert x.shape == (224, 224, 10) and x.dtype == np.complex128
+    assert rel_l2(x, xo) <= TOL_XUPDATE
+
+
+def test_admm_loop_batched_slices_are_independent(q, ops):
+    from oracle.admm import pnp_admm
+    P, Po = ops["spiral"]
+    Fo, Xgt, Y, X0 = make_problem(Po, 22, S=2)
+    Y[:, 1] *= 3.0  # different dynamic range per slice: min/max normalisation must be per slice
+    X0 = Fo.adjoint(Y)
+    param = {"iter": 4, "gamma": 0.05, "denoiser_type": "single_level"}
+    x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=box_denoiser, X0=X0))
+    for s in range(2):
+        xo = pnp_admm(Y[:, s], dict(param, F=Fo, net=box_denoiser, X0=X0[..., s]), solver="exact")
+        assert rel_l2(x[..., s], xo) <= TOL_XUPDATE
+
+
+def test_admm_iter_counts_zero_and_one(q, ops):
+    P, Po = ops["spiral"]
+    Fo, Xgt, Y, X0 = make_problem(Po, 23)
+    for it in (0, 1):
+        x = q.PnP_ADMM(Y, {"iter": it, "gamma": 0.05, "F": q.fft_operator(P), "net": box_denoiser, "X0": X0})
+        assert rel_l2(x, X0) <= 1e-6  # x_1 = X0 because A X0 = y (PnP_ADMM.m:102 with a zero residual)
+
+
+@pytest.mark.parametrize("dtype", ["single_level", "multi_level"])
+def test_admm_loop_with_builtin_unetres(q, ops, dtype):
+    """End to end: the on-device loop (K1 + K3) against the oracle loop with the CPU UNetRes."""
+    from oracle import unetres
+    from oracle.admm import pnp_admm
+    P, Po = ops["spiral"]
+    Fo, Xgt, Y, X0 = make_problem(Po, 24)
+    in_nc = 10 if dtype == "single_level" else 11
+    sd = unetres.make_state_dict(in_nc, seed=0)
+    net = q.UNetRes(sd, in_nc=in_nc)
+    param = {"iter": 3, "gamma": 0.05, "X0": X0, "denoiser_type": dtype}
+    if dtype == "multi_level":
+        param["noise_map"] = q.build_noise_map(0.01, 224, 224)
+    xo = pnp_admm(Y, dict(param, F=Fo, net=lambda v: unetres.denoise_matlab_layout(sd, v)), solver="exact")
+    x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=net))
+    assert rel_l2(x, xo) <= 1e-4  # bounded by the denoiser tolerance
+
+
+# ---------------------------------------------------------------------------------------------
+def test_error_behaviour(q):
+    V = np.eye(10)
+    with pytest.raises(q.QmriError):
+        q.setup_subsampling_spiralgrided(224, 224, 771, np.ones((10, 10)))       # unsupported V
+    with pytest.raises(q.QmriError):
+        q.setup_subsampling_spiralgrided(128, 128, 771, V)                       # unsupported size
+    with pytest.raises(q.QmriError):
+        q.setup_subsampling_epi(224, 224, 0.0, V)
+    P = q.setup_subsampling_epi(224, 224, 1 / 65, V)
+    F = q.fft_operator(P)
+    with pytest.raises(ValueError):
+        F.forward(np.zeros((224, 224, 9)))
+    with pytest.raises(KeyError):
+        q.PnP_ADMM(np.zeros(P.nmeas, complex), {"iter": 1, "gamma": 0.05, "F": F, "X0": np.zeros((224, 224, 10))})
+    with pytest.raises(q.QmriError):
+        q.PnP_ADMM(np.zeros(P.nmeas, complex), {"iter": 1, "gamma": 0.0, "F": F, "X0": np.zeros((224, 224, 10)), "net": box_denoiser})
+
+    def bad(v):
+        raise RuntimeError("denoiser exploded")
+    with pytest.raises(RuntimeError, match="exploded"):
+        q.PnP_ADMM(np.zeros(P.nmeas, complex), {"iter": 2, "gamma": 0.05, "F": F, "X0": np.ones((224, 224, 10)), "net": bad})
