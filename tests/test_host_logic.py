@@ -1,0 +1,42 @@
+"""Host-side logic of the Python mirror that needs no GPU: argument validation, key order, helpers."""
+import numpy as np
+import pytest
+
+import qmri_b200 as q
+from oracle import unetres
+
+
+def test_state_dict_key_order_matches_reference_order():
+    for in_nc in (10, 11):
+        mine = q.state_dict_keys(in_nc)
+        ref = unetres.layer_names(in_nc)
+        assert [k for k, _ in mine] == [k for k, *_ in ref]
+        sd = unetres.make_state_dict(in_nc, seed=0)
+        for k, shape in mine:
+            assert tuple(sd[k].shape) == shape
+
+
+def test_build_noise_map():
+    nm = q.build_noise_map(0.01, 224, 224)
+    assert nm.shape == (224, 224) and nm.dtype == np.float64 and np.all(nm == 0.01)
+
+
+def test_param_validation_without_gpu():
+    from qmri_b200.admm import _make_params
+    with pytest.raises(KeyError, match="param.iter"):
+        _make_params({"gamma": 0.05}, [])
+    with pytest.raises(TypeError, match="fft_operator"):
+        _make_params({"iter": 1, "gamma": 0.05, "F": object(), "X0": 0, "net": lambda v: v}, [])
+
+
+def test_denoise_wrapper_validates_input():
+    class Net:
+        def denoise(self, A):
+            return A[:, :, :10]
+    with pytest.raises(ValueError):
+        q.denoiseImage_PnP_ADMM(np.full((8, 8, 10), np.nan), Net())
+    with pytest.raises(ValueError):
+        q.denoiseImage_PnP_ADMM(np.zeros((0, 8, 10)), Net())
+    A = np.random.default_rng(0).random((8, 8, 10))
+    assert np.array_equal(q.denoiseImage_PnP_ADMM(A, Net(), True, False), A)
+    assert np.allclose(q.denoiseImage_PnP_ADMM(A, Net(), True, True), 0)

@@ -1,0 +1,82 @@
+"""CPU emulation of the K1 kernel (same phase functions / tables as the CUDA kernel, thread by
+thread) against the float64 oracle.  This is how the kernel arithmetic is checked in a container
+without a GPU; the GPU parity tests repeat the comparison on the real kernel."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import PKG, rel_l2
+from oracle import sampling
+from oracle.xupdate import xupdate_exact
+
+LIB = os.path.join(PKG, "lib", "libk1emu.so")
+fp = ctypes.POINTER(ctypes.c_float)
+
+
+def P(a):
+    return a.ctypes.data_as(fp) if a is not None else None
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(LIB):
+        pytest.skip("libk1emu.so not built (run __graft_entry__.build())")
+    lib = ctypes.CDLL(LIB)
+    lib.k1emu_masks.restype = ctypes.c_int
+    lib.k1emu_masks.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.k1emu_run.restype = ctypes.c_int
+    lib.k1emu_run.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [fp] * 4 + [ctypes.c_float] + [fp] * 4
+    return lib
+
+
+def planar(a):
+    a = np.transpose(a, (2, 1, 0))
+    return np.ascontiguousarray(a.real.astype(np.float32)), np.ascontiguousarray(a.imag.astype(np.float32))
+
+
+def unplanar(re, im):
+    return np.transpose(re.astype(np.float64) + 1j * im.astype(np.float64), (2, 1, 0))
+
+
+@pytest.mark.parametrize("pat,arg", [(0, 771.0), (1, 1 / 65)])
+def test_cxx_mask_constructors_equal_oracle(emu, pat, arg):
+    for L in (10, 50):
+        Po = (sampling.setup_subsampling_spiralgrided(224, 224, 771, np.eye(L)) if pat == 0
+              else sampling.setup_subsampling_epi(224, 224, 1 / 65, np.eye(L)))
+        n = emu.k1emu_masks(pat, 224, arg, L, None, None)
+        idx = np.zeros(n, np.int32)
+        fptr = np.zeros(L + 1, np.int64)
+        emu.k1emu_masks(pat, 224, arg, L, idx.ctypes.data, fptr.ctypes.data)
+        assert np.array_equal(idx, Po.idx) and np.array_equal(fptr, Po.frame_ptr)
+
+
+@pytest.mark.parametrize("pat,arg,mc", [(0, 771.0, 28), (0, 771.0, 56), (1, 1 / 65, 28)])
+def test_k1_arithmetic_all_modes(emu, pat, arg, mc):
+    C = 3
+    Po = (sampling.setup_subsampling_spiralgrided(224, 224, 771, np.eye(C)) if pat == 0
+          else sampling.setup_subsampling_epi(224, 224, 1 / 65, np.eye(C)))
+    F = sampling.FOperator(Po)
+    n = Po.nmeas
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal((224, 224, C)) + 1j * rng.standard_normal((224, 224, C))
+    zr, zi = planar(z)
+    yout = np.zeros((n, 2), np.float32)
+    emu.k1emu_run(2, mc, pat, arg, C, 1, P(zr), P(zi), None, None, 0.05, None, None, P(yout), None)
+    assert rel_l2(yout[:, 0] + 1j * yout[:, 1], F.forward(z)) < 1e-6
+    y = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    y32 = np.stack([y.real, y.imag], 1).astype(np.float32)
+    ore, oim = np.zeros_like(zr), np.zeros_like(zr)
+    emu.k1emu_run(3, mc, pat, arg, C, 1, None, None, None, P(y32), 0.05, P(ore), P(oim), None, None)
+    assert rel_l2(unplanar(ore, oim), F.adjoint(y)) < 1e-6
+    mm = np.zeros(2, np.float32)
+    emu.k1emu_run(1, mc, pat, arg, C, 1, P(zr), P(zi), None, P(y32), 0.05, P(ore), P(oim), None, P(mm))
+    xe = xupdate_exact(F, y, z, 0.05)
+    assert rel_l2(unplanar(ore, oim), xe) < 1e-6
+    assert abs(mm[0] - xe.real.min()) < 1e-5 and abs(mm[1] - xe.real.max()) < 1e-5
+    v = rng.standard_normal((224, 224, C))
+    vr, _ = planar(v + 0j)
+    emu.k1emu_run(0, mc, pat, arg, C, 1, P(zr), P(zi), P(vr), P(y32), 0.05, P(ore), P(oim), None, P(mm))
+    x = xupdate_exact(F, y, 2 * v - z, 0.05)
+    assert rel_l2(unplanar(ore, oim), x + (z - v)) < 1e-6   # w' = x + u, u = w - v
