@@ -13,10 +13,44 @@
 #include <math.h>
 #include <string.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "conv_kernels.h"
 
 namespace {
+
+// activation access that understands both storage formats: fp32, or split bf16 (hi + lo planes)
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t u) { return __uint_as_float((uint32_t)u << 16); }
+__device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
+    __nv_bfloat16 b = __float2bfloat16_rn(f);
+    return *reinterpret_cast<uint16_t*>(&b);
+}
+__device__ __forceinline__ float4 ld_act4(const float* f32, const uint16_t* hi, const uint16_t* lo, size_t idx) {
+    if (!hi) return __ldg(reinterpret_cast<const float4*>(f32 + idx));
+    uint2 a = __ldg(reinterpret_cast<const uint2*>(hi + idx)), b = __ldg(reinterpret_cast<const uint2*>(lo + idx));
+    float4 r;
+    r.x = __uint_as_float(a.x << 16) + __uint_as_float(b.x << 16);
+    r.y = __uint_as_float(a.x & 0xffff0000u) + __uint_as_float(b.x & 0xffff0000u);
+    r.z = __uint_as_float(a.y << 16) + __uint_as_float(b.y << 16);
+    r.w = __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u);
+    return r;
+}
+__device__ __forceinline__ void st_act4(float* f32, uint16_t* hi, uint16_t* lo, size_t idx, float4 v) {
+    if (!hi) {
+        *reinterpret_cast<float4*>(f32 + idx) = v;
+        return;
+    }
+    float f[4] = {v.x, v.y, v.z, v.w};
+    uint16_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = float_to_bf16_bits(f[i]);
+        l[i] = float_to_bf16_bits(f[i] - bf16_bits_to_float(h[i]));
+    }
+    *reinterpret_cast<uint2*>(hi + idx) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2*>(lo + idx) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
 
 // ---------------------------------------------------------------------------------------
 // 3x3, stride 1, pad 1, Cin % 8 == 0, Cout % 64 == 0.  CTA: 8 x 16 output pixels x 64 couts.
@@ -154,14 +188,14 @@ __global__ void __launch_bounds__(256) resample_gemm_fp32_kernel(ConvParams p) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lm < Mtot) {
                 int k = k0 + lk;
-                const float* src;
+                size_t src;
                 if (up) {
-                    src = p.in + (((size_t)ls * Hi + ly) * Wi + lx) * p.Cin + k;
+                    src = (((size_t)ls * Hi + ly) * Wi + lx) * p.Cin + k;
                 } else {
                     int tap = k / p.Cin, ci = k % p.Cin;
-                    src = p.in + (((size_t)ls * Hi + 2 * ly + (tap >> 1)) * Wi + 2 * lx + (tap & 1)) * p.Cin + ci;
+                    src = (((size_t)ls * Hi + 2 * ly + (tap >> 1)) * Wi + 2 * lx + (tap & 1)) * p.Cin + ci;
                 }
-                v = __ldg(reinterpret_cast<const float4*>(src));
+                v = ld_act4(p.in, p.in_hi, p.in_lo, src);
             }
             As[lk + 0][lr] = v.x;
             As[lk + 1][lr] = v.y;
@@ -202,7 +236,7 @@ __global__ void __launch_bounds__(256) resample_gemm_fp32_kernel(ConvParams p) {
         } else {
             o = (((size_t)s * Ho + y) * Wo + x) * p.Cout + n;
         }
-        *reinterpret_cast<float4*>(p.out + o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        st_act4(p.out, p.out_hi, p.out_lo, o, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
     }
 }
 
@@ -260,9 +294,10 @@ __global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
             }
         }
         if (y < p.H && x < p.W) {
-            float4* o = reinterpret_cast<float4*>(p.nhwc + (((size_t)s * p.H + y) * p.W + x) * 64 + cb);
+            const size_t o = (((size_t)s * p.H + y) * p.W + x) * 64 + cb;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            for (int q = 0; q < 4; ++q)
+                st_act4(p.nhwc, p.nhwc_hi, p.nhwc_lo, o + 4 * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
         }
     }
 }
@@ -279,7 +314,7 @@ __global__ void __launch_bounds__(256) tail_fp32_kernel(HeadTailParams p) {
     const int ty0 = (blockIdx.x / tiles_x) * 16, tx0 = (blockIdx.x % tiles_x) * 16;
     const int s = blockIdx.z;
     const int ty = tid >> 4, tx = tid & 15;
-    const float* in = p.nhwc + (size_t)s * p.H * p.W * 64;
+    const size_t in_off = (size_t)s * p.H * p.W * 64;
     float acc[10];
 #pragma unroll
     for (int j = 0; j < 10; ++j) acc[j] = 0.f;
@@ -291,7 +326,7 @@ __global__ void __launch_bounds__(256) tail_fp32_kernel(HeadTailParams p) {
             int y = ty0 + py - 1, x = tx0 + px - 1;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (y >= 0 && y < p.H && x >= 0 && x < p.W)
-                v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)y * p.W + x) * 64 + c0 + 4 * q));
+                v = ld_act4(p.nhwc, p.nhwc_hi, p.nhwc_lo, in_off + ((size_t)y * p.W + x) * 64 + c0 + 4 * q);
             patch[4 * q + 0][py][px] = v.x;
             patch[4 * q + 1][py][px] = v.y;
             patch[4 * q + 2][py][px] = v.z;

@@ -494,7 +494,9 @@ extern "C" int qmri_unetres_destroy(qmri_net* net) {
 }
 extern "C" int qmri_unetres_set_precision(qmri_net* net, int mode) {
     if (!net) return qmri_fail(QMRI_EINVAL, "null net");
-    if (mode != 0) return qmri_fail(QMRI_EUNSUPPORTED, "denoiser precision mode %d is not available in this build", mode);
+    if (mode != 0 && mode != 1) return qmri_fail(QMRI_EINVAL, "denoiser precision mode must be 0 (fp32) or 1 (tcgen05 split-bf16), got %d", mode);
+    if (mode == 1 && !net->tc_available)
+        return qmri_fail(QMRI_EUNSUPPORTED, "tensor mode unavailable: cuTensorMapEncodeTiled could not be resolved");
     net->precision = mode;
     return QMRI_OK;
 }

@@ -76,6 +76,36 @@ void pack_layer(const LayerDesc& d, const float* w, int orient, std::vector<floa
     }
 }
 
+uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);  // round to nearest even
+}
+float bf2f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// 3x3 conv weights for the tensor path: [co][tap][ci] (K-major rows, tap-major K), split hi / lo
+void pack_layer_tc(const LayerDesc& d, const float* w, int orient, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+    const int ci_n = d.cin, co_n = d.cout;
+    hi.assign((size_t)9 * ci_n * co_n, 0);
+    lo.assign((size_t)9 * ci_n * co_n, 0);
+    for (int co = 0; co < co_n; ++co)
+        for (int ci = 0; ci < ci_n; ++ci)
+            for (int r = 0; r < 3; ++r)
+                for (int s = 0; s < 3; ++s) {
+                    int ry = orient ? s : r, sx = orient ? r : s;
+                    float v = w[(((size_t)co * ci_n + ci) * 3 + r) * 3 + s];
+                    size_t o = ((size_t)co * 9 + (ry * 3 + sx)) * ci_n + ci;
+                    hi[o] = f2bf(v);
+                    lo[o] = f2bf(v - bf2f(hi[o]));
+                }
+}
+
 }  // namespace
 
 size_t unetres_weight_count(int in_nc, int layer) {
@@ -115,6 +145,30 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
                 return qmri_fail(QMRI_ECUDA, "weight upload failed: %s", cudaGetErrorString(e));
             }
         }
+        // tensor-mode copies of the 58 3x3 convs
+        net->wtc_hi[o].assign(64, nullptr);
+        net->wtc_lo[o].assign(64, nullptr);
+        net->wmap_hi[o].resize(64);
+        net->wmap_lo[o].resize(64);
+        std::vector<uint16_t> hi, lo;
+        for (int l = 0; l < 64; ++l) {
+            if (L[l].kind != 0) continue;
+            pack_layer_tc(L[l], weights[l], o, hi, lo);
+            int r = dev_alloc(&net->wtc_hi[o][l], hi.size()) | dev_alloc(&net->wtc_lo[o][l], lo.size());
+            if (r) {
+                unetres_free(net);
+                return r;
+            }
+            cudaMemcpy(net->wtc_hi[o][l], hi.data(), hi.size() * 2, cudaMemcpyHostToDevice);
+            cudaMemcpy(net->wtc_lo[o][l], lo.data(), lo.size() * 2, cudaMemcpyHostToDevice);
+            const int BN = tc_block_n(L[l].cout);
+            r = tc_make_weight_map(&net->wmap_hi[o][l], net->wtc_hi[o][l], 9 * L[l].cin, L[l].cout, BN) |
+                tc_make_weight_map(&net->wmap_lo[o][l], net->wtc_lo[o][l], 9 * L[l].cin, L[l].cout, BN);
+            if (r) {
+                net->tc_available = false;  // driver entry point missing: tensor mode stays off, fp32 mode works
+                break;
+            }
+        }
     }
     *out = net;
     return QMRI_OK;
@@ -123,9 +177,14 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
 void unetres_free(qmri_net* net) {
     if (!net) return;
     DevSetter ds(net->ctx->device);
-    for (int o = 0; o < 2; ++o)
+    for (int o = 0; o < 2; ++o) {
         for (float* p : net->w[o])
             if (p) cudaFree(p);
+        for (uint16_t* p : net->wtc_hi[o])
+            if (p) cudaFree(p);
+        for (uint16_t* p : net->wtc_lo[o])
+            if (p) cudaFree(p);
+    }
     if (net->ws) cudaFree(net->ws);
     if (net->io) cudaFree(net->io);
     delete net;
@@ -223,20 +282,133 @@ static int forward_chunk(qmri_net* net, const float* in, float* out, const float
     return QMRI_OK;
 }
 
+// ---- tensor mode ---------------------------------------------------------------------------
+// Workspace buffers are laid out for the FULL chunk (net->chunk slices): buffer b of level l holds
+// level_elems * chunk elements; as split bf16 that is a hi plane followed by a lo plane.
+static void tc_buffers(qmri_net* net, int H, int W, uint16_t* hi[3][4], uint16_t* lo[3][4]) {
+    float* base = net->ws;
+    for (int l = 0; l < 4; ++l) {
+        size_t n = level_elems(l, H, W) * net->chunk;
+        for (int b = 0; b < 3; ++b) {
+            hi[b][l] = reinterpret_cast<uint16_t*>(base + (size_t)b * n);
+            lo[b][l] = hi[b][l] + n;
+        }
+        base += 3 * n;
+    }
+}
+
+static int build_act_maps(qmri_net* net, int H, int W) {
+    if (net->amap_ws == net->ws && net->amap_chunk == net->chunk && net->amap_H == H && net->amap_W == W) return QMRI_OK;
+    uint16_t *hi[3][4], *lo[3][4];
+    tc_buffers(net, H, W, hi, lo);
+    for (int l = 0; l < 4; ++l) {
+        int BW, BH;
+        tc_tile_shape(W >> l, H >> l, &BW, &BH);
+        for (int b = 0; b < 3; ++b) {
+            QCHECK(tc_make_act_map(&net->amap[b][l][0], hi[b][l], net->chunk, H >> l, W >> l, NC[l], BW, BH));
+            QCHECK(tc_make_act_map(&net->amap[b][l][1], lo[b][l], net->chunk, H >> l, W >> l, NC[l], BW, BH));
+        }
+    }
+    net->amap_ws = net->ws;
+    net->amap_chunk = net->chunk;
+    net->amap_H = H;
+    net->amap_W = W;
+    return QMRI_OK;
+}
+
+static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const float* minmax, const float* noise_map,
+                            int S, int H, int W, int orient) {
+    qmri_ctx* ctx = net->ctx;
+    uint16_t *hi[3][4], *lo[3][4];
+    tc_buffers(net, H, W, hi, lo);
+    enum { BX = 0, BA = 1, BT = 2 };
+    int roleA[4] = {BA, BA, BA, BA}, roleT[4] = {BT, BT, BT, BT};  // which physical buffer plays A / T per level
+    const std::vector<float*>& w = net->w[orient];
+    int li = 0;
+    if (net->in_nc == 11 && !noise_map) return qmri_fail(QMRI_EINVAL, "11-channel denoiser needs a noise map");
+    HeadTailParams hp = {};
+    hp.planar_in = in;
+    hp.noise_map = (net->in_nc == 11) ? noise_map : nullptr;
+    hp.nhwc_hi = hi[BX][0];
+    hp.nhwc_lo = lo[BX][0];
+    hp.w = w[li++];
+    hp.minmax = minmax;
+    hp.S = S; hp.H = H; hp.W = W; hp.Cin = net->in_nc;
+    QCHECK(head_fp32(ctx, hp));
+
+    // 3x3 conv: src buffer -> dst buffer at `lvl`, optional residual buffers (physical ids, -1 = none)
+    auto conv = [&](int lvl, int src, int dst, int layer, int relu, int r1, int r2) {
+        TcConvParams p = {};
+        p.out_hi = hi[dst][lvl]; p.out_lo = lo[dst][lvl];
+        p.res1_hi = r1 >= 0 ? hi[r1][lvl] : nullptr; p.res1_lo = r1 >= 0 ? lo[r1][lvl] : nullptr;
+        p.res2_hi = r2 >= 0 ? hi[r2][lvl] : nullptr; p.res2_lo = r2 >= 0 ? lo[r2][lvl] : nullptr;
+        p.S = S; p.H = H >> lvl; p.W = W >> lvl; p.Cin = NC[lvl]; p.Cout = NC[lvl];
+        tc_tile_shape(p.W, p.H, &p.BW, &p.BH);
+        p.tiles_x = (p.W + p.BW - 1) / p.BW;
+        p.tiles_y = (p.H + p.BH - 1) / p.BH;
+        p.relu = relu;
+        return conv3x3_tc(ctx, &net->amap[src][lvl][0], &net->amap[src][lvl][1], &net->wmap_hi[orient][layer],
+                          &net->wmap_lo[orient][layer], p);
+    };
+    auto resample = [&](int lvl_in, int src, int lvl_out, int dst, int layer, int up) {
+        ConvParams p = {};
+        p.in_hi = hi[src][lvl_in]; p.in_lo = lo[src][lvl_in];
+        p.out_hi = hi[dst][lvl_out]; p.out_lo = lo[dst][lvl_out];
+        p.w = w[layer];
+        p.S = S; p.H = H >> lvl_in; p.W = W >> lvl_in; p.Cin = NC[lvl_in]; p.Cout = NC[lvl_out]; p.mode = up;
+        return resample_fp32(ctx, p);
+    };
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        for (int b = 0; b < 4; ++b) {
+            int xin = (b == 0) ? BX : roleA[lvl];
+            QCHECK(conv(lvl, xin, roleT[lvl], li, 1, -1, -1)); ++li;
+            QCHECK(conv(lvl, roleT[lvl], roleA[lvl], li, 0, xin, -1)); ++li;
+        }
+        QCHECK(resample(lvl, roleA[lvl], lvl + 1, BX, li, 0)); ++li;
+    }
+    for (int b = 0; b < 4; ++b) {
+        int xin = (b == 0) ? BX : roleA[3];
+        QCHECK(conv(3, xin, roleT[3], li, 1, -1, -1)); ++li;
+        QCHECK(conv(3, roleT[3], roleA[3], li, 0, xin, (b == 3) ? BX : -1)); ++li;
+    }
+    for (int lvl = 2; lvl >= 0; --lvl) {
+        QCHECK(resample(lvl + 1, roleA[lvl + 1], lvl, roleT[lvl], li, 1)); ++li;
+        int tmp = roleA[lvl]; roleA[lvl] = roleT[lvl]; roleT[lvl] = tmp;
+        for (int b = 0; b < 4; ++b) {
+            QCHECK(conv(lvl, roleA[lvl], roleT[lvl], li, 1, -1, -1)); ++li;
+            QCHECK(conv(lvl, roleT[lvl], roleA[lvl], li, 0, roleA[lvl], (b == 3) ? BX : -1)); ++li;
+        }
+    }
+    HeadTailParams tp = {};
+    tp.nhwc_hi = hi[roleA[0]][0];
+    tp.nhwc_lo = lo[roleA[0]][0];
+    tp.planar_out = out;
+    tp.w = w[li++];
+    tp.minmax = minmax;
+    tp.S = S; tp.H = H; tp.W = W; tp.Cin = 64;
+    QCHECK(tail_fp32(ctx, tp));
+    return QMRI_OK;
+}
+
 int unetres_forward_dev(qmri_net* net, const float* in, float* out, const float* minmax, const float* noise_map,
                         int S, int H, int W, int orient) {
     if (!net || !in || !out) return qmri_fail(QMRI_EINVAL, "unetres forward: null argument");
     if (S <= 0) return QMRI_OK;
     if (H % 8 || W % 8 || H < 8 || W < 8) return qmri_fail(QMRI_EINVAL, "UNetRes needs H, W multiples of 8 (got %d x %d)", H, W);
-    if (net->precision != 0)
-        return qmri_fail(QMRI_EUNSUPPORTED, "denoiser precision mode %d is not available in this build", net->precision);
+    if (net->precision == 1 && !net->tc_available)
+        return qmri_fail(QMRI_EUNSUPPORTED, "tensor mode unavailable: cuTensorMapEncodeTiled could not be resolved");
     DevSetter ds(net->ctx->device);
     QCHECK(unetres_reserve(net, S, H, W));
+    if (net->precision == 1) QCHECK(build_act_maps(net, H, W));
     const int Cpl = (net->in_nc == 11) ? 10 : net->in_nc;
     for (int s0 = 0; s0 < S; s0 += net->chunk) {
         int n = (S - s0 < net->chunk) ? S - s0 : net->chunk;
-        QCHECK(forward_chunk(net, in + (size_t)s0 * Cpl * H * W, out + (size_t)s0 * 10 * H * W,
-                             minmax ? minmax + 2 * s0 : nullptr, noise_map, n, H, W, orient));
+        if (net->precision == 1)
+            QCHECK(forward_chunk_tc(net, in + (size_t)s0 * Cpl * H * W, out + (size_t)s0 * 10 * H * W,
+                                    minmax ? minmax + 2 * s0 : nullptr, noise_map, n, H, W, orient));
+        else
+            QCHECK(forward_chunk(net, in + (size_t)s0 * Cpl * H * W, out + (size_t)s0 * 10 * H * W,
+                                 minmax ? minmax + 2 * s0 : nullptr, noise_map, n, H, W, orient));
     }
     return QMRI_OK;
 }

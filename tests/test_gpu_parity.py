@@ -223,8 +223,10 @@ def nets(q):
     return q.UNetRes(sd, in_nc=10), sd
 
 
-@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 64, 40)])
-def test_denoiser_matches_cpu_forward(q, nets, shape):
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 64, 40), (1, 224, 224), (9, 16, 24)])
+def test_denoiser_matches_cpu_forward(q, nets, shape, precision):
+    """fp32 = CUDA-core exact mode; tc = tcgen05 split-bf16 tensor mode.  Same 1e-4 bar for both."""
     import torch
     from oracle import unetres
     net, sd = nets
@@ -233,9 +235,15 @@ def test_denoiser_matches_cpu_forward(q, nets, shape):
     x = torch.rand(S, 10, H, W)
     with torch.no_grad():
         ref = unetres.unetres_forward(sd, x).numpy()
-    out = net.forward(x.numpy())
+    net.set_precision(precision)
+    try:
+        out = net.forward(x.numpy())
+    finally:
+        net.set_precision("fp32")
     assert out.shape == ref.shape
-    assert rel_l2(out, ref) <= TOL_DENOISER
+    err = rel_l2(out, ref)
+    print(f"denoiser {precision} {shape}: rel-L2 {err:.3e}")
+    assert err <= TOL_DENOISER
 
 
 def test_denoiser_matlab_layout_and_wrapper(q, nets):
@@ -314,8 +322,8 @@ def test_admm_iter_counts_zero_and_one(q, ops):
         assert rel_l2(x, X0) <= 1e-6  # x_1 = X0 because A X0 = y (PnP_ADMM.m:102 with a zero residual)
 
 
-@pytest.mark.parametrize("dtype", ["single_level", "multi_level"])
-def test_admm_loop_with_builtin_unetres(q, ops, dtype):
+@pytest.mark.parametrize("dtype,precision", [("single_level", "fp32"), ("multi_level", "fp32"), ("single_level", "tc")])
+def test_admm_loop_with_builtin_unetres(q, ops, dtype, precision):
     """End to end: the on-device loop (K1 + K3) against the oracle loop with the CPU UNetRes."""
     from oracle import unetres
     from oracle.admm import pnp_admm
@@ -324,6 +332,7 @@ def test_admm_loop_with_builtin_unetres(q, ops, dtype):
     in_nc = 10 if dtype == "single_level" else 11
     sd = unetres.make_state_dict(in_nc, seed=0)
     net = q.UNetRes(sd, in_nc=in_nc)
+    net.set_precision(precision)
     param = {"iter": 3, "gamma": 0.05, "X0": X0, "denoiser_type": dtype}
     if dtype == "multi_level":
         param["noise_map"] = q.build_noise_map(0.01, 224, 224)
