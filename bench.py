@@ -262,7 +262,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "tensor", "kernel": "UNetRes forward (64 conv launches; 3x3 convs = 97% of flops)", "achieved": fwd_tflops,
                 "peak": tensor_peak, "unit": "TFLOP/s", "frac": fwd_tflops / tensor_peak, "traffic": None,
                 "peak_source": f"{peaks['src']} dense bf16 (sustained); the fp32 exact mode runs on CUDA cores, see DESIGN.md",
-                "ms_per_forward": ms_fwd / 5, "precision_mode": args.precision or "fp32"}
+                "ms_per_forward": ms_fwd / 5, "precision_mode": args.precision}
     # K1 at a batch larger than L2 (algorithmic bytes: 20 B per pixel-channel per iteration)
     roof_k1 = None
     if rank == 0 and not args.skip_extra:
@@ -315,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": "ADMM slice-iterations/s (224x224x10 slice batch)", "value": value, "unit": "slice-iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (x-update fp32 FFT; denoiser " + (args.precision or "fp32") + ")", "data": "synthetic",
+            "dtype": "f32 (x-update fp32 FFT; denoiser " + args.precision + ")", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: PnP-ADMM, spiral 771 (6184 meas/slice), rho 0.05, random-init UNetRes 10->10",
                        "slices_per_gpu": S, "iters_per_step": iters, "l2": "256 MiB buffer written between steps",
                        "parallelism": f"slice-sharded x{world}, no collective"},
@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slices", type=int, default=1, help="slices per GPU (configs[1] = 1; configs[2] = 15)")
     ap.add_argument("--iters", type=int, default=100, help="ADMM iterations per reconstruction (param.iter)")
-    ap.add_argument("--precision", default="", help="denoiser precision mode: '' / fp32 / tc")
+    ap.add_argument("--precision", default="tc", choices=["tc", "fp32"], help="denoiser precision mode: tc (tcgen05 split-bf16, default) / fp32 (CUDA cores)")
     ap.add_argument("--k1-slices", type=int, default=120)
     ap.add_argument("--match-atoms", type=int, default=100000)
     ap.add_argument("--cpu-iters", type=int, default=12)

@@ -35,7 +35,8 @@ struct HeadTailParams {
     uint16_t* nhwc_lo = nullptr;
 };
 
-// tcgen05 implicit-GEMM 3x3 conv on split-bf16 planes (conv_tc.cu)
+// tcgen05 implicit-GEMM convolutions on split-bf16 planes (conv_tc.cu)
+enum { TC_CONV3X3 = 0, TC_DOWN2X2 = 1, TC_UP2X2 = 2 };
 struct TcConvParams {
     uint16_t* out_hi;
     uint16_t* out_lo;
@@ -43,9 +44,17 @@ struct TcConvParams {
     const uint16_t* res1_lo;
     const uint16_t* res2_hi;   // optional U-skip
     const uint16_t* res2_lo;
-    int S, H, W, Cin, Cout;
+    int mode;                  // TC_CONV3X3 / TC_DOWN2X2 / TC_UP2X2
+    int S, H, W;               // pixel grid of the GEMM's M dimension: conv3x3 image, down OUTPUT, up INPUT
+    int Cin, Cout;             // channels per tap / per output pixel
     int BW, BH, tiles_x, tiles_y;
     int relu;
+    float* partial;            // split-K workspace (tc_partial_elems floats) and tickets (tc_ticket_count ints, zeroed once)
+    int* tickets;
+    const void* mapA_hi[4];    // CUtensorMap*: [0] for conv3x3 / up, one per tap (dy*2+dx) for down
+    const void* mapA_lo[4];
+    const void* mapB_hi;       // weights [N][K] K-major, box = tc_block_n(Cout) rows
+    const void* mapB_lo;
 };
 
 int conv3x3_fp32(qmri_ctx* ctx, const ConvParams& p);
@@ -53,9 +62,11 @@ int resample_fp32(qmri_ctx* ctx, const ConvParams& p);
 int head_fp32(qmri_ctx* ctx, const HeadTailParams& p);
 int tail_fp32(qmri_ctx* ctx, const HeadTailParams& p);
 int tc_make_act_map(void* out_map, const void* base, int S, int H, int W, int C, int BW, int BH);
-int tc_make_weight_map(void* out_map, const void* base, int K, int Cout, int BN);
+int tc_make_down_map(void* out_map, const void* base, int S, int H, int W, int C, int dy, int dx, int BW, int BH);
+int tc_make_weight_map(void* out_map, const void* base, int K, int N, int BN);
 int tc_tile_shape(int W, int H, int* BW, int* BH);
 int tc_block_n(int Cout);
-int conv3x3_tc(qmri_ctx* ctx, const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo,
-               const TcConvParams& p);
+size_t tc_partial_elems(int sm_count);
+size_t tc_ticket_count(int sm_count);
+int conv_tc(qmri_ctx* ctx, const TcConvParams& p);
 int normalize_planar(qmri_ctx* ctx, const float* in, float* out, const float* minmax, size_t per_slice, int S, int undo);

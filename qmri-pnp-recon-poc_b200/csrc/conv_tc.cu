@@ -1,7 +1,8 @@
-// K3 (tensor mode) - DRUNet 3x3 convolutions as a tcgen05 implicit GEMM with split-bf16 operands.
+// K3 (tensor mode) - the DRUNet convolutions as tcgen05 implicit GEMMs with split-bf16 operands.
 //
-// Reference being replaced: the 58 bias-free 3x3 convolutions of UNetRes
-//   PyTorch_Denoiser/zhang_dpir_testing_code/network_unet.py:106-117, basicblock.py:61-98,211-223.
+// Reference being replaced: the bias-free convolutions of UNetRes
+//   PyTorch_Denoiser/zhang_dpir_testing_code/network_unet.py:106-117, basicblock.py:61-98,211-223
+//   (58 x 3x3 s1 p1), :437-443 (3 x Conv2d 2x2 s2) and :413-419 (3 x ConvTranspose2d 2x2 s2).
 //
 // Precision: the parity bar is 1e-4 relative L2 against the fp32 CPU forward.  Single-pass TF32
 // (5e-4) and bf16 (4e-3) operands fail it, so every fp32 value a is carried as
@@ -10,15 +11,32 @@
 // K step; the dropped a_lo*w_lo term is 2^-18 relative).
 //
 // Data layout: activations are two bf16 planes (hi, lo), each [S][Y][X][C] (channels innermost,
-// 2 B): same bytes as one fp32 tensor.  Weights are [Cout][9*Cin] K-major, tap-major K, hi / lo.
+// 2 B): same bytes as one fp32 tensor.  Weights are K-major rows [N][K], hi / lo planes.
 //
-// Kernel: persistent, warp-specialised.  GEMM tile = 128 output pixels (a BH x BW patch of one
-// slice) x BN output channels; K loop over 9 taps x Cin/64.  For each k-block the producer thread
-// issues 4 TMA tile loads (A_hi, A_lo as 4-D boxes of the shifted patch - out-of-image pixels are
-// zero-filled by TMA, which is the conv's zero padding; B_hi, B_lo as 2-D boxes) into a 128B-swizzled
-// shared-memory ring; one MMA thread issues 12 tcgen05.mma (M128 x BN x K16) per k-block into one of
-// two TMEM accumulators; four epilogue warps drain the other accumulator with tcgen05.ld, add the
-// residuals, apply ReLU, re-split to (hi, lo) and store.
+// One kernel, three GEMM views (MODE):
+//   0  3x3 s1 p1     M = pixels, N = Cout, K = 9 taps x Cin.  The A tile of tap (dy, dx) is the
+//                    4-D TMA box of the pixel patch shifted by (dx, dy); out-of-image pixels are
+//                    zero-filled by TMA, which is the conv's zero padding.
+//   1  2x2 s2 conv   M = output pixels, N = Cout, K = 4 taps x Cin.  Tap (dy, dx) has its own
+//                    tensor map: the input viewed with pixel strides 2 and base offset (dy, dx).
+//   2  2x2 s2 convT  M = input pixels, N = 4 phases x Cout, K = Cin.  The epilogue scatters the
+//                    N block of phase (dy, dx) to output pixel (2y + dy, 2x + dx).
+//
+// Kernel: persistent, warp-specialised.  GEMM tile = 128 pixels (a BH x BW patch of one slice) x BN
+// columns.  Per k-block (one tap, 64 channels) the producer thread issues 4 TMA tile loads (A_hi,
+// A_lo, B_hi, B_lo) into a 128B-swizzled shared-memory ring; one MMA thread issues 12 tcgen05.mma
+// (M128 x BN x K16) per k-block into one of two TMEM accumulators; four epilogue warps drain the
+// other accumulator with tcgen05.ld, add the residuals, apply ReLU, re-split to (hi, lo) and store.
+//
+// Split-K: when a layer has fewer tiles than SMs (deep U-Net levels at small slice batches) the K loop
+// is divided over `nsplit` CTAs per tile.  Every CTA writes its fp32 partial tile to an L2-resident
+// workspace; the last epilogue warp to arrive for a 32-row quarter of the tile (atomic ticket) sums
+// the partials in split order (deterministic) and runs the normal epilogue.
+//
+// Measured on B200 (profiles/): the kernel is bound by L2 -> SM operand traffic (~12 TB/s chip-wide),
+// not by the tensor pipe.  An A-tile "halo" variant that reused one shared-memory patch for all 9
+// taps through 128-byte-offset (not 1024-byte aligned) UMMA descriptors gave correct results but ran
+// its MMAs ~2x slower than aligned descriptors (with all loads disabled), and was removed.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
@@ -129,29 +147,187 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& a, float& b) {
     b = __uint_as_float(u & 0xffff0000u);
 }
 
+
+struct TcMaps {
+    CUtensorMap a_hi[4], a_lo[4];  // MODE 1 uses one pair per tap, the others only [0]
+    CUtensorMap b_hi, b_lo;
+};
+
+// device-side copy of TcConvParams (without the host tensor-map pointers)
+struct TcK {
+    uint16_t *out_hi, *out_lo;
+    const uint16_t *res1_hi, *res1_lo, *res2_hi, *res2_lo;
+    float* partial;
+    int* tickets;
+    int S, H, W, Cin, Cout;
+    int BW, BH, tiles_x, tiles_y;
+    int relu, nsplit;
+};
+
+// v[0..8) += hi + lo (8 bf16 pairs)
+__device__ __forceinline__ void add_split8(float* v, const uint4 a, const uint4 b) {
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float h0, h1, l0, l1;
+        unpack_bf16(ua[j], h0, h1);
+        unpack_bf16(ub[j], l0, l1);
+        v[2 * j] += h0 + l0;
+        v[2 * j + 1] += h1 + l1;
+    }
+}
+
+// ReLU, split to (hi, lo) and store 16 consecutive channels
+__device__ __forceinline__ void store_split16(uint16_t* oh, uint16_t* ol, const float* v, int relu) {
+    uint32_t ph[8], pl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a = v[2 * j], b = v[2 * j + 1];
+        if (relu) {
+            a = fmaxf(a, 0.f);
+            b = fmaxf(b, 0.f);
+        }
+        ph[j] = pack_bf16(a, b);
+        float ha, hb;
+        unpack_bf16(ph[j], ha, hb);
+        pl[j] = pack_bf16(a - ha, b - hb);
+    }
+    uint4* o4h = reinterpret_cast<uint4*>(oh);
+    uint4* o4l = reinterpret_cast<uint4*>(ol);
+    o4h[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    o4h[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+    o4l[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    o4l[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+}
+
+// Epilogue of one 128 x BN tile (no split-K).  This thread owns one output pixel (TMEM lane) and BN
+// channels.  The ResBlock residual of the pixel (BN hi + BN lo bf16 = BN/4 uint4) is fetched into
+// registers BEFORE waiting for the accumulator, so its global-memory latency hides behind the tile's
+// MMA main loop; the accumulator is then drained 32 columns at a time (two tcgen05.ld in flight).
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcConvParams p) {
+__device__ __forceinline__ void tc_epilogue_tile(const TcK& p, uint32_t taddr, size_t o, bool ok, uint64_t* tfull_bar, uint32_t parity) {
+    uint4 rh[BN / 8], rl[BN / 8];
+    const bool has_r1 = ok && (p.res1_hi != nullptr);
+    if (has_r1) {
+        const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o);
+        const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o);
+#pragma unroll
+        for (int i = 0; i < BN / 8; ++i) {
+            rh[i] = gh[i];
+            rl[i] = gl[i];
+        }
+    }
+    mbar_wait(tfull_bar, parity);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[2][16];
+        tc_ld16(taddr + c0, acc[0]);
+        tc_ld16(taddr + c0 + 16, acc[1]);
+        tc_wait_ld();
+        if (ok) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int cc = c0 + 16 * half;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[half][j]);
+                if (has_r1) {
+                    add_split8(v, rh[cc / 8], rl[cc / 8]);
+                    add_split8(v + 8, rh[cc / 8 + 1], rl[cc / 8 + 1]);
+                }
+                if (p.res2_hi) {  // U-skip: only the last conv of a level
+                    const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o + cc);
+                    const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o + cc);
+                    add_split8(v, gh[0], gl[0]);
+                    add_split8(v + 8, gh[1], gl[1]);
+                }
+                store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
+            }
+        }
+    }
+}
+
+// Split-K epilogue, phase 1: park this CTA's partial accumulator row in the workspace.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_park(uint32_t taddr, float* prow, uint64_t* tfull_bar, uint32_t parity) {
+    mbar_wait(tfull_bar, parity);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[2][16];
+        tc_ld16(taddr + c0, acc[0]);
+        tc_ld16(taddr + c0 + 16, acc[1]);
+        tc_wait_ld();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float4* d = reinterpret_cast<float4*>(prow + c0 + 16 * half);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                d[q] = make_float4(__uint_as_float(acc[half][4 * q]), __uint_as_float(acc[half][4 * q + 1]),
+                                   __uint_as_float(acc[half][4 * q + 2]), __uint_as_float(acc[half][4 * q + 3]));
+        }
+    }
+}
+
+// Split-K epilogue, phase 2 (last arriver of the row quarter): sum the partials in split order and finish.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_reduce(const TcK& p, const float* prow0, size_t o) {
+    const size_t split_stride = (size_t)TC_BM * BN;
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += 16) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int s = 0; s < p.nsplit; ++s) {
+            const float4* src = reinterpret_cast<const float4*>(prow0 + (size_t)s * split_stride + cc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = __ldcg(src + q);  // written by other SMs: read through L2
+                v[4 * q] += t.x;
+                v[4 * q + 1] += t.y;
+                v[4 * q + 2] += t.z;
+                v[4 * q + 3] += t.w;
+            }
+        }
+        if (p.res1_hi) {
+            const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o + cc);
+            const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o + cc);
+            add_split8(v, gh[0], gl[0]);
+            add_split8(v + 8, gh[1], gl[1]);
+        }
+        if (p.res2_hi) {
+            const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o + cc);
+            const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o + cc);
+            add_split8(v, gh[0], gl[0]);
+            add_split8(v + 8, gh[1], gl[1]);
+        }
+        store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
+    }
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcMaps maps, const TcK p) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int TAPS = (MODE == 0) ? 9 : (MODE == 1) ? 4 : 1;
     extern __shared__ unsigned char tc_smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     const uint32_t raw = smem_u32(tc_smem_raw);
     unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;                  // [STAGES]
-    uint64_t* empty = bars + STAGES;        // [STAGES]
-    uint64_t* tfull = bars + 2 * STAGES;    // [2]
+    uint64_t* full = bars;                     // [STAGES]
+    uint64_t* empty = bars + STAGES;           // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;       // [2]
     uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KB = 9 * (p.Cin / TC_BK);
     const int cblocks = p.Cin / TC_BK;
-    const int NT = p.Cout / BN;
+    const int KB = TAPS * cblocks;
+    const int NT = ((MODE == 2) ? 4 * p.Cout : p.Cout) / BN;
     const int tiles_xy = p.tiles_x * p.tiles_y;
-    const int total_tiles = tiles_xy * NT * p.S;
+    const int total_work = tiles_xy * NT * p.S * p.nsplit;  // work item = (tile, K split)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -163,10 +339,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             mbar_init(&tempty[a], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        tma_prefetch_desc(&tmA_hi);
-        tma_prefetch_desc(&tmA_lo);
-        tma_prefetch_desc(&tmB_hi);
-        tma_prefetch_desc(&tmB_lo);
+        tma_prefetch_desc(&maps.a_hi[0]);
+        tma_prefetch_desc(&maps.a_lo[0]);
+        tma_prefetch_desc(&maps.b_hi);
+        tma_prefetch_desc(&maps.b_lo);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS));
@@ -182,26 +358,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int t = w / p.nsplit, split = w - t * p.nsplit;
                 const int nt = t % NT;
-                int r = t / NT;
+                const int r = t / NT;
                 const int txy = r % tiles_xy;
                 const int s = r / tiles_xy;
                 const int x0 = (txy % p.tiles_x) * p.BW, y0 = (txy / p.tiles_x) * p.BH;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    for (int cb = 0; cb < cblocks; ++cb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        unsigned char* st = smem + (size_t)stage * Cfg::STAGE_BYTES;
-                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                        tma_load_4d(st, &tmA_hi, &full[stage], cb * TC_BK, x0 + dx, y0 + dy, s);
-                        tma_load_4d(st + A_TILE_BYTES, &tmA_lo, &full[stage], cb * TC_BK, x0 + dx, y0 + dy, s);
-                        tma_load_2d(st + 2 * A_TILE_BYTES, &tmB_hi, &full[stage], tap * p.Cin + cb * TC_BK, nt * BN);
-                        tma_load_2d(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, &tmB_lo, &full[stage], tap * p.Cin + cb * TC_BK, nt * BN);
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                const int kb0 = (split * KB) / p.nsplit, kb1 = ((split + 1) * KB) / p.nsplit;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* st = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    if (MODE == 0) {
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        tma_load_4d(st, &maps.a_hi[0], &full[stage], cb * TC_BK, x0 + dx, y0 + dy, s);
+                        tma_load_4d(st + A_TILE_BYTES, &maps.a_lo[0], &full[stage], cb * TC_BK, x0 + dx, y0 + dy, s);
+                    } else if (MODE == 1) {
+                        tma_load_4d(st, &maps.a_hi[tap], &full[stage], cb * TC_BK, x0, y0, s);
+                        tma_load_4d(st + A_TILE_BYTES, &maps.a_lo[tap], &full[stage], cb * TC_BK, x0, y0, s);
+                    } else {
+                        tma_load_4d(st, &maps.a_hi[0], &full[stage], cb * TC_BK, x0, y0, s);
+                        tma_load_4d(st + A_TILE_BYTES, &maps.a_lo[0], &full[stage], cb * TC_BK, x0, y0, s);
+                    }
+                    tma_load_2d(st + 2 * A_TILE_BYTES, &maps.b_hi, &full[stage], kb * TC_BK, nt * BN);
+                    tma_load_2d(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, &maps.b_lo, &full[stage], kb * TC_BK, nt * BN);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
@@ -214,13 +399,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+                const int t = w / p.nsplit, split = w - t * p.nsplit;
+                const int kb0 = (split * KB) / p.nsplit, kb1 = ((split + 1) * KB) / p.nsplit;
                 const int ab = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tempty[ab], aphase ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BN);
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
@@ -229,7 +416,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes along K inside the swizzle atom (16-byte units)
-                        tc_mma(tmem_d, a_hi + ko, b_hi + ko, idesc, (kb | k) ? 1u : 0u);
+                        tc_mma(tmem_d, a_hi + ko, b_hi + ko, idesc, ((kb - kb0) | k) ? 1u : 0u);
                         tc_mma(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
                         tc_mma(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
                     }
@@ -247,87 +434,48 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const int lg = warp & 3;
         const int row = lg * 32 + lane;  // row of the 128-pixel tile
         int it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+            const int t = w / p.nsplit, split = w - t * p.nsplit;
             const int ab = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int nt = t % NT;
-            int r = t / NT;
+            const int r = t / NT;
             const int txy = r % tiles_xy;
             const int s = r / tiles_xy;
             const int x = (txy % p.tiles_x) * p.BW + row % p.BW;
             const int y = (txy / p.tiles_x) * p.BH + row / p.BW;
             const bool ok = (x < p.W) && (y < p.H);
-            const size_t o = (((size_t)s * p.H + y) * p.W + x) * p.Cout + (size_t)nt * BN;
-            mbar_wait(&tfull[ab], aphase);
-            tc_fence_after();
+            size_t o;
+            if (MODE == 2) {  // N block nt belongs to output phase (dy, dx); scatter to (2y + dy, 2x + dx)
+                const int n0 = nt * BN;
+                const int ph = n0 / p.Cout, co0 = n0 - ph * p.Cout;
+                o = (((size_t)s * 2 * p.H + 2 * y + (ph >> 1)) * (2 * p.W) + 2 * x + (ph & 1)) * p.Cout + co0;
+            } else {
+                o = (((size_t)s * p.H + y) * p.W + x) * p.Cout + (size_t)nt * BN;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * BN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t acc[16];
-                tc_ld16(taddr + c0, acc);
-                tc_wait_ld();
-                if (ok) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-                    if (p.res1_hi) {
-                        const uint4* rh = reinterpret_cast<const uint4*>(p.res1_hi + o + c0);
-                        const uint4* rl = reinterpret_cast<const uint4*>(p.res1_lo + o + c0);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 a = rh[h], b = rl[h];
-                            uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float h0, h1, l0, l1;
-                                unpack_bf16(ua[j], h0, h1);
-                                unpack_bf16(ub[j], l0, l1);
-                                v[8 * h + 2 * j] += h0 + l0;
-                                v[8 * h + 2 * j + 1] += h1 + l1;
-                            }
-                        }
-                    }
-                    if (p.res2_hi) {
-                        const uint4* rh = reinterpret_cast<const uint4*>(p.res2_hi + o + c0);
-                        const uint4* rl = reinterpret_cast<const uint4*>(p.res2_lo + o + c0);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 a = rh[h], b = rl[h];
-                            uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float h0, h1, l0, l1;
-                                unpack_bf16(ua[j], h0, h1);
-                                unpack_bf16(ub[j], l0, l1);
-                                v[8 * h + 2 * j] += h0 + l0;
-                                v[8 * h + 2 * j + 1] += h1 + l1;
-                            }
-                        }
-                    }
-                    uint32_t ph[8], pl[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float a = v[2 * j], b = v[2 * j + 1];
-                        if (p.relu) {
-                            a = fmaxf(a, 0.f);
-                            b = fmaxf(b, 0.f);
-                        }
-                        ph[j] = pack_bf16(a, b);
-                        float ha, hb;
-                        unpack_bf16(ph[j], ha, hb);
-                        pl[j] = pack_bf16(a - ha, b - hb);
-                    }
-                    uint4* oh = reinterpret_cast<uint4*>(p.out_hi + o + c0);
-                    uint4* ol = reinterpret_cast<uint4*>(p.out_lo + o + c0);
-                    oh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                    oh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-                    ol[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                    ol[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            if (p.nsplit == 1) {
+                tc_epilogue_tile<BN>(p, taddr, o, ok, &tfull[ab], aphase);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[ab]);
+            } else {
+                float* prow0 = p.partial + ((size_t)t * p.nsplit * TC_BM + row) * BN;  // split 0's row of this tile
+                tc_epilogue_park<BN>(taddr, prow0 + (size_t)split * TC_BM * BN, &tfull[ab], aphase);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[ab]);
+                __threadfence();
+                __syncwarp();
+                int old = 0;
+                if (lane == 0) old = atomicAdd(&p.tickets[t * 4 + lg], 1);
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old == p.nsplit - 1) {  // every other split of this row quarter is parked
+                    __threadfence();
+                    if (lane == 0) p.tickets[t * 4 + lg] = 0;  // ready for the next launch
+                    if (ok) tc_epilogue_reduce<BN>(p, prow0, o);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[ab]);
         }
     }
     tc_fence_before();
@@ -354,13 +502,13 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-}  // namespace
-
-int tc_make_act_map(void* out_map, const void* base, int S, int H, int W, int C, int BW, int BH) {
+// 4-D activation map over pixels (x, y) with pixel strides (sx, sy) elements of C channels
+int make_act_map(void* out_map, const void* base, int S, int H, int W, int C, size_t row_pitch_px, size_t slice_pitch_px, int px_stride,
+                 int BW, int BH) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return qmri_fail(QMRI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)S};
-    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint64_t gstr[3] = {(cuuint64_t)px_stride * C * 2, (cuuint64_t)row_pitch_px * C * 2, (cuuint64_t)slice_pitch_px * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)BW, (cuuint32_t)BH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
@@ -370,17 +518,29 @@ int tc_make_act_map(void* out_map, const void* base, int S, int H, int W, int C,
     return QMRI_OK;
 }
 
-int tc_make_weight_map(void* out_map, const void* base, int K, int Cout, int BN) {
+}  // namespace
+
+int tc_make_act_map(void* out_map, const void* base, int S, int H, int W, int C, int BW, int BH) {
+    return make_act_map(out_map, base, S, H, W, C, (size_t)W, (size_t)H * W, 1, BW, BH);
+}
+
+// tap (dy, dx) of a 2x2 stride-2 conv: the [S][H][W][C] input seen as an (H/2) x (W/2) image of the pixels (2y + dy, 2x + dx)
+int tc_make_down_map(void* out_map, const void* base, int S, int H, int W, int C, int dy, int dx, int BW, int BH) {
+    const uint16_t* b = reinterpret_cast<const uint16_t*>(base) + ((size_t)dy * W + dx) * C;
+    return make_act_map(out_map, b, S, H / 2, W / 2, C, (size_t)2 * W, (size_t)H * W, 2, BW, BH);
+}
+
+int tc_make_weight_map(void* out_map, const void* base, int K, int N, int BN) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return qmri_fail(QMRI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return qmri_fail(QMRI_ECUDA, "cuTensorMapEncodeTiled(weights %d x %d) failed: %d", Cout, K, (int)r);
+    if (r != CUDA_SUCCESS) return qmri_fail(QMRI_ECUDA, "cuTensorMapEncodeTiled(weights %d x %d) failed: %d", N, K, (int)r);
     return QMRI_OK;
 }
 
@@ -404,31 +564,64 @@ int tc_tile_shape(int W, int H, int* BW, int* BH) {
 
 int tc_block_n(int Cout) { return Cout == 64 ? 64 : 128; }
 
-int conv3x3_tc(qmri_ctx* ctx, const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo,
-               const TcConvParams& p) {
-    if (p.Cin % TC_BK) return qmri_fail(QMRI_EINVAL, "conv3x3_tc: Cin %% 64");
-    const int BN = tc_block_n(p.Cout);
-    if (p.Cout % BN) return qmri_fail(QMRI_EINVAL, "conv3x3_tc: Cout %% %d", BN);
-    const int total = p.tiles_x * p.tiles_y * (p.Cout / BN) * p.S;
-    const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-    const CUtensorMap& a_hi = *(const CUtensorMap*)mapA_hi;
-    const CUtensorMap& a_lo = *(const CUtensorMap*)mapA_lo;
-    const CUtensorMap& b_hi = *(const CUtensorMap*)mapB_hi;
-    const CUtensorMap& b_lo = *(const CUtensorMap*)mapB_lo;
-    static bool cfg64 = false, cfg128 = false;
-    if (BN == 64) {
-        if (!cfg64) {
-            QCUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<64>::SMEM));
-            cfg64 = true;
-        }
-        conv3x3_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::SMEM, ctx->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
-    } else {
-        if (!cfg128) {
-            QCUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<128>::SMEM));
-            cfg128 = true;
-        }
-        conv3x3_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM, ctx->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+size_t tc_partial_elems(int sm_count) { return (size_t)sm_count * TC_BM * 128; }
+size_t tc_ticket_count(int sm_count) { return (size_t)sm_count * 4; }
+
+template <int BN, int MODE>
+static int launch_tc(qmri_ctx* ctx, const TcMaps& maps, const TcK& k, int grid) {
+    static bool configured = false;
+    if (!configured) {
+        QCUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM));
+        configured = true;
     }
+    tc_conv_kernel<BN, MODE><<<grid, TC_THREADS, TcCfg<BN>::SMEM, ctx->stream>>>(maps, k);
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
+}
+
+int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
+    if (p.Cin % TC_BK) return qmri_fail(QMRI_EINVAL, "conv_tc: Cin %% 64");
+    if (p.mode < 0 || p.mode > 2) return qmri_fail(QMRI_EINVAL, "conv_tc: mode %d", p.mode);
+    const int BN = tc_block_n(p.Cout);
+    const int ncols = (p.mode == TC_UP2X2) ? 4 * p.Cout : p.Cout;
+    if (ncols % BN) return qmri_fail(QMRI_EINVAL, "conv_tc: N %% %d", BN);
+    const int taps = (p.mode == TC_CONV3X3) ? 9 : (p.mode == TC_DOWN2X2) ? 4 : 1;
+    const int KB = taps * (p.Cin / TC_BK);
+    const int total_tiles = p.tiles_x * p.tiles_y * (ncols / BN) * p.S;
+    // split K when the layer cannot fill the SMs (>= 4 k-blocks per split, workspace sized for sm_count work items)
+    int nsplit = 1;
+    if (p.partial && p.tickets && 2 * total_tiles <= ctx->sm_count) {
+        nsplit = ctx->sm_count / total_tiles;
+        if (nsplit > KB / 4) nsplit = KB / 4;
+        if (nsplit > 8) nsplit = 8;
+        if (nsplit < 1) nsplit = 1;
+    }
+    const int work = total_tiles * nsplit;
+    const int grid = work < ctx->sm_count ? work : ctx->sm_count;
+    TcMaps maps;
+    const int na = (p.mode == TC_DOWN2X2) ? 4 : 1;
+    for (int i = 0; i < 4; ++i) {
+        const int j = i < na ? i : 0;
+        if (!p.mapA_hi[j] || !p.mapA_lo[j]) return qmri_fail(QMRI_EINVAL, "conv_tc: missing activation tensor map");
+        maps.a_hi[i] = *(const CUtensorMap*)p.mapA_hi[j];
+        maps.a_lo[i] = *(const CUtensorMap*)p.mapA_lo[j];
+    }
+    maps.b_hi = *(const CUtensorMap*)p.mapB_hi;
+    maps.b_lo = *(const CUtensorMap*)p.mapB_lo;
+    TcK k;
+    k.out_hi = p.out_hi; k.out_lo = p.out_lo;
+    k.res1_hi = p.res1_hi; k.res1_lo = p.res1_lo;
+    k.res2_hi = p.res2_hi; k.res2_lo = p.res2_lo;
+    k.partial = p.partial; k.tickets = p.tickets;
+    k.S = p.S; k.H = p.H; k.W = p.W; k.Cin = p.Cin; k.Cout = p.Cout;
+    k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
+    k.relu = p.relu; k.nsplit = nsplit;
+    if (BN == 64) {
+        if (p.mode == TC_CONV3X3) return launch_tc<64, 0>(ctx, maps, k, grid);
+        if (p.mode == TC_DOWN2X2) return launch_tc<64, 1>(ctx, maps, k, grid);
+        return launch_tc<64, 2>(ctx, maps, k, grid);
+    }
+    if (p.mode == TC_CONV3X3) return launch_tc<128, 0>(ctx, maps, k, grid);
+    if (p.mode == TC_DOWN2X2) return launch_tc<128, 1>(ctx, maps, k, grid);
+    return launch_tc<128, 2>(ctx, maps, k, grid);
 }

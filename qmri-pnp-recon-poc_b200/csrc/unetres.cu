@@ -8,6 +8,7 @@
 // Layer order == state_dict() key order (64 bias-free weight tensors):
 //   0 head | 1-8 down1 res, 9 down1 strideconv | 10-17, 18 | 19-26, 27 | 28-35 body |
 //   36 up3 convT, 37-44 res | 45, 46-53 | 54, 55-62 | 63 tail
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -89,18 +90,30 @@ float bf2f(uint16_t h) {
     return f;
 }
 
-// 3x3 conv weights for the tensor path: [co][tap][ci] (K-major rows, tap-major K), split hi / lo
+// weights for the tensor path as K-major GEMM rows, split hi / lo:
+//   3x3 conv   [co][tap][ci]            (tap-major K)
+//   down 2x2   [co][tap][ci]
+//   up 2x2 T   [phase * Cout + co][ci]  (phase = output sub-pixel (dy, dx))
 void pack_layer_tc(const LayerDesc& d, const float* w, int orient, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
     const int ci_n = d.cin, co_n = d.cout;
-    hi.assign((size_t)9 * ci_n * co_n, 0);
-    lo.assign((size_t)9 * ci_n * co_n, 0);
+    const int kk = (d.kind == 0) ? 3 : 2, taps = kk * kk;
+    hi.assign((size_t)taps * ci_n * co_n, 0);
+    lo.assign((size_t)taps * ci_n * co_n, 0);
     for (int co = 0; co < co_n; ++co)
         for (int ci = 0; ci < ci_n; ++ci)
-            for (int r = 0; r < 3; ++r)
-                for (int s = 0; s < 3; ++s) {
-                    int ry = orient ? s : r, sx = orient ? r : s;
-                    float v = w[(((size_t)co * ci_n + ci) * 3 + r) * 3 + s];
-                    size_t o = ((size_t)co * 9 + (ry * 3 + sx)) * ci_n + ci;
+            for (int r = 0; r < kk; ++r)
+                for (int s = 0; s < kk; ++s) {
+                    const int ry = orient ? s : r, sx = orient ? r : s;
+                    const int tap = ry * kk + sx;
+                    float v;
+                    size_t o;
+                    if (d.kind == 2) {  // ConvTranspose2d weight is [ci][co][kh][kw]
+                        v = w[(((size_t)ci * co_n + co) * kk + r) * kk + s];
+                        o = ((size_t)tap * co_n + co) * ci_n + ci;
+                    } else {
+                        v = w[(((size_t)co * ci_n + ci) * kk + r) * kk + s];
+                        o = ((size_t)co * taps + tap) * ci_n + ci;
+                    }
                     hi[o] = f2bf(v);
                     lo[o] = f2bf(v - bf2f(hi[o]));
                 }
@@ -145,14 +158,14 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
                 return qmri_fail(QMRI_ECUDA, "weight upload failed: %s", cudaGetErrorString(e));
             }
         }
-        // tensor-mode copies of the 58 3x3 convs
+        // tensor-mode copies of the 58 3x3 convs and the six 2x2 stride-2 resampling convs
         net->wtc_hi[o].assign(64, nullptr);
         net->wtc_lo[o].assign(64, nullptr);
         net->wmap_hi[o].resize(64);
         net->wmap_lo[o].resize(64);
         std::vector<uint16_t> hi, lo;
-        for (int l = 0; l < 64; ++l) {
-            if (L[l].kind != 0) continue;
+        for (int l = 0; l < 64 && net->tc_available; ++l) {
+            if (L[l].kind > 2) continue;
             pack_layer_tc(L[l], weights[l], o, hi, lo);
             int r = dev_alloc(&net->wtc_hi[o][l], hi.size()) | dev_alloc(&net->wtc_lo[o][l], lo.size());
             if (r) {
@@ -162,13 +175,23 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
             cudaMemcpy(net->wtc_hi[o][l], hi.data(), hi.size() * 2, cudaMemcpyHostToDevice);
             cudaMemcpy(net->wtc_lo[o][l], lo.data(), lo.size() * 2, cudaMemcpyHostToDevice);
             const int BN = tc_block_n(L[l].cout);
-            r = tc_make_weight_map(&net->wmap_hi[o][l], net->wtc_hi[o][l], 9 * L[l].cin, L[l].cout, BN) |
-                tc_make_weight_map(&net->wmap_lo[o][l], net->wtc_lo[o][l], 9 * L[l].cin, L[l].cout, BN);
-            if (r) {
-                net->tc_available = false;  // driver entry point missing: tensor mode stays off, fp32 mode works
-                break;
-            }
+            const int K = (L[l].kind == 0 ? 9 : L[l].kind == 1 ? 4 : 1) * L[l].cin;
+            const int N = (L[l].kind == 2 ? 4 : 1) * L[l].cout;
+            r = tc_make_weight_map(&net->wmap_hi[o][l], net->wtc_hi[o][l], K, N, BN) |
+                tc_make_weight_map(&net->wmap_lo[o][l], net->wtc_lo[o][l], K, N, BN);
+            if (r) net->tc_available = false;  // driver entry point missing: tensor mode off, exact fp32 mode still works
         }
+    }
+    if (net->tc_available) {
+        const size_t np = tc_partial_elems(ctx->sm_count), nt = tc_ticket_count(ctx->sm_count);
+        int r = dev_alloc(&net->tc_partial, np) | dev_alloc(&net->tc_tickets, nt);
+        if (r) {
+            unetres_free(net);
+            return r;
+        }
+        cudaMemset(net->tc_tickets, 0, nt * sizeof(int));
+    } else {
+        net->precision = 0;
     }
     *out = net;
     return QMRI_OK;
@@ -187,6 +210,8 @@ void unetres_free(qmri_net* net) {
     }
     if (net->ws) cudaFree(net->ws);
     if (net->io) cudaFree(net->io);
+    if (net->tc_partial) cudaFree(net->tc_partial);
+    if (net->tc_tickets) cudaFree(net->tc_tickets);
     delete net;
 }
 
@@ -307,6 +332,14 @@ static int build_act_maps(qmri_net* net, int H, int W) {
         for (int b = 0; b < 3; ++b) {
             QCHECK(tc_make_act_map(&net->amap[b][l][0], hi[b][l], net->chunk, H >> l, W >> l, NC[l], BW, BH));
             QCHECK(tc_make_act_map(&net->amap[b][l][1], lo[b][l], net->chunk, H >> l, W >> l, NC[l], BW, BH));
+            if (l < 3) {  // stride-2 tap views feeding the down conv to level l + 1
+                int DW, DH;
+                tc_tile_shape(W >> (l + 1), H >> (l + 1), &DW, &DH);
+                for (int tap = 0; tap < 4; ++tap) {
+                    QCHECK(tc_make_down_map(&net->amap_down[b][l][tap][0], hi[b][l], net->chunk, H >> l, W >> l, NC[l], tap >> 1, tap & 1, DW, DH));
+                    QCHECK(tc_make_down_map(&net->amap_down[b][l][tap][1], lo[b][l], net->chunk, H >> l, W >> l, NC[l], tap >> 1, tap & 1, DW, DH));
+                }
+            }
         }
     }
     net->amap_ws = net->ws;
@@ -316,9 +349,41 @@ static int build_act_maps(qmri_net* net, int H, int W) {
     return QMRI_OK;
 }
 
+struct LayerProf {
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    bool on = false;
+    void mark(qmri_ctx* ctx, const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        ev.push_back(e);
+        names.push_back(name);
+    }
+    void report(int S) {
+        if (!on || ev.empty()) return;
+        cudaEventSynchronize(ev.back());
+        double tot = 0;
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, "[qmri profile] S=%d %-10s %8.1f us\n", S, names[i], ms * 1e3);
+            tot += ms;
+        }
+        fprintf(stderr, "[qmri profile] S=%d total %8.1f us\n", S, tot * 1e3);
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        names.clear();
+    }
+};
+
 static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const float* minmax, const float* noise_map,
                             int S, int H, int W, int orient) {
     qmri_ctx* ctx = net->ctx;
+    LayerProf prof;
+    prof.on = getenv("QMRI_PROFILE") != nullptr;
+    prof.mark(ctx, "start");
     uint16_t *hi[3][4], *lo[3][4];
     tc_buffers(net, H, W, hi, lo);
     enum { BX = 0, BA = 1, BT = 2 };
@@ -335,48 +400,75 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
     hp.minmax = minmax;
     hp.S = S; hp.H = H; hp.W = W; hp.Cin = net->in_nc;
     QCHECK(head_fp32(ctx, hp));
+    prof.mark(ctx, "head");
 
+    auto tiles = [&](TcConvParams& p) {
+        tc_tile_shape(p.W, p.H, &p.BW, &p.BH);
+        p.tiles_x = (p.W + p.BW - 1) / p.BW;
+        p.tiles_y = (p.H + p.BH - 1) / p.BH;
+        p.partial = net->tc_partial;
+        p.tickets = net->tc_tickets;
+    };
     // 3x3 conv: src buffer -> dst buffer at `lvl`, optional residual buffers (physical ids, -1 = none)
     auto conv = [&](int lvl, int src, int dst, int layer, int relu, int r1, int r2) {
         TcConvParams p = {};
+        p.mode = TC_CONV3X3;
         p.out_hi = hi[dst][lvl]; p.out_lo = lo[dst][lvl];
         p.res1_hi = r1 >= 0 ? hi[r1][lvl] : nullptr; p.res1_lo = r1 >= 0 ? lo[r1][lvl] : nullptr;
         p.res2_hi = r2 >= 0 ? hi[r2][lvl] : nullptr; p.res2_lo = r2 >= 0 ? lo[r2][lvl] : nullptr;
         p.S = S; p.H = H >> lvl; p.W = W >> lvl; p.Cin = NC[lvl]; p.Cout = NC[lvl];
-        tc_tile_shape(p.W, p.H, &p.BW, &p.BH);
-        p.tiles_x = (p.W + p.BW - 1) / p.BW;
-        p.tiles_y = (p.H + p.BH - 1) / p.BH;
         p.relu = relu;
-        return conv3x3_tc(ctx, &net->amap[src][lvl][0], &net->amap[src][lvl][1], &net->wmap_hi[orient][layer],
-                          &net->wmap_lo[orient][layer], p);
+        tiles(p);
+        p.mapA_hi[0] = &net->amap[src][lvl][0]; p.mapA_lo[0] = &net->amap[src][lvl][1];
+        p.mapB_hi = &net->wmap_hi[orient][layer]; p.mapB_lo = &net->wmap_lo[orient][layer];
+        return conv_tc(ctx, p);
     };
+    // 2x2 stride-2 conv (up = 0: lvl_in -> lvl_in + 1) or transposed conv (up = 1: lvl_in -> lvl_in - 1)
     auto resample = [&](int lvl_in, int src, int lvl_out, int dst, int layer, int up) {
-        ConvParams p = {};
-        p.in_hi = hi[src][lvl_in]; p.in_lo = lo[src][lvl_in];
+        TcConvParams p = {};
+        p.mode = up ? TC_UP2X2 : TC_DOWN2X2;
         p.out_hi = hi[dst][lvl_out]; p.out_lo = lo[dst][lvl_out];
-        p.w = w[layer];
-        p.S = S; p.H = H >> lvl_in; p.W = W >> lvl_in; p.Cin = NC[lvl_in]; p.Cout = NC[lvl_out]; p.mode = up;
-        return resample_fp32(ctx, p);
+        const int lm = up ? lvl_in : lvl_out;  // level of the GEMM's pixel grid
+        p.S = S; p.H = H >> lm; p.W = W >> lm; p.Cin = NC[lvl_in]; p.Cout = NC[lvl_out];
+        tiles(p);
+        if (up) {
+            p.mapA_hi[0] = &net->amap[src][lvl_in][0]; p.mapA_lo[0] = &net->amap[src][lvl_in][1];
+        } else {
+            for (int tap = 0; tap < 4; ++tap) {
+                p.mapA_hi[tap] = &net->amap_down[src][lvl_in][tap][0];
+                p.mapA_lo[tap] = &net->amap_down[src][lvl_in][tap][1];
+            }
+        }
+        p.mapB_hi = &net->wmap_hi[orient][layer]; p.mapB_lo = &net->wmap_lo[orient][layer];
+        return conv_tc(ctx, p);
     };
     for (int lvl = 0; lvl < 3; ++lvl) {
         for (int b = 0; b < 4; ++b) {
             int xin = (b == 0) ? BX : roleA[lvl];
             QCHECK(conv(lvl, xin, roleT[lvl], li, 1, -1, -1)); ++li;
+            prof.mark(ctx, lvl == 0 ? "conv L0" : lvl == 1 ? "conv L1" : "conv L2");
             QCHECK(conv(lvl, roleT[lvl], roleA[lvl], li, 0, xin, -1)); ++li;
+            prof.mark(ctx, lvl == 0 ? "conv L0 r" : lvl == 1 ? "conv L1 r" : "conv L2 r");
         }
         QCHECK(resample(lvl, roleA[lvl], lvl + 1, BX, li, 0)); ++li;
+        prof.mark(ctx, "down");
     }
     for (int b = 0; b < 4; ++b) {
         int xin = (b == 0) ? BX : roleA[3];
         QCHECK(conv(3, xin, roleT[3], li, 1, -1, -1)); ++li;
+        prof.mark(ctx, "conv L3");
         QCHECK(conv(3, roleT[3], roleA[3], li, 0, xin, (b == 3) ? BX : -1)); ++li;
+        prof.mark(ctx, "conv L3 r");
     }
     for (int lvl = 2; lvl >= 0; --lvl) {
         QCHECK(resample(lvl + 1, roleA[lvl + 1], lvl, roleT[lvl], li, 1)); ++li;
+        prof.mark(ctx, "up");
         int tmp = roleA[lvl]; roleA[lvl] = roleT[lvl]; roleT[lvl] = tmp;
         for (int b = 0; b < 4; ++b) {
             QCHECK(conv(lvl, roleA[lvl], roleT[lvl], li, 1, -1, -1)); ++li;
+            prof.mark(ctx, lvl == 0 ? "conv L0" : lvl == 1 ? "conv L1" : "conv L2");
             QCHECK(conv(lvl, roleT[lvl], roleA[lvl], li, 0, roleA[lvl], (b == 3) ? BX : -1)); ++li;
+            prof.mark(ctx, lvl == 0 ? "conv L0 r" : lvl == 1 ? "conv L1 r" : "conv L2 r");
         }
     }
     HeadTailParams tp = {};
@@ -387,6 +479,8 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
     tp.minmax = minmax;
     tp.S = S; tp.H = H; tp.W = W; tp.Cin = 64;
     QCHECK(tail_fp32(ctx, tp));
+    prof.mark(ctx, "tail");
+    prof.report(S);
     return QMRI_OK;
 }
 

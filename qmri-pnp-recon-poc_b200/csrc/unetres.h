@@ -14,7 +14,7 @@ struct alignas(64) TMap {
 struct qmri_net {
     qmri_ctx* ctx = nullptr;
     int in_nc = 10;
-    int precision = 0;          // 0 = fp32 CUDA cores, 1 = tcgen05 split-bf16
+    int precision = 1;          // 0 = fp32 CUDA cores (exact mode), 1 = tcgen05 split-bf16 (default; 5e-6 rel-L2)
     bool tc_available = true;
     std::vector<float*> w[2];   // packed device weights per layer, [0] PyTorch planes, [1] MATLAB planes
     float* ws = nullptr;        // activation workspace
@@ -23,11 +23,15 @@ struct qmri_net {
     int chunk = 0;
     float* io = nullptr;        // staging for the host entry points
     size_t io_elems = 0;
-    // tensor mode (tcgen05, split bf16): K-major weights [Cout][9*Cin] as hi / lo planes and their TMA maps
+    // tensor mode (tcgen05, split bf16): K-major weights [N][K] as hi / lo planes and their TMA maps
+    // (3x3: [Cout][9*Cin]; down 2x2: [Cout][4*Cin]; up 2x2 transposed: [4*Cout][Cin])
     std::vector<uint16_t*> wtc_hi[2], wtc_lo[2];
     std::vector<TMap> wmap_hi[2], wmap_lo[2];
     // activation TMA maps per workspace buffer (X, A, T) x level x plane (hi, lo); rebuilt when the workspace moves
     TMap amap[3][4][2];
+    TMap amap_down[3][3][4][2];  // buffer x input level x tap (dy*2+dx) x plane: stride-2 views for the 2x2 s2 convs
+    float* tc_partial = nullptr; // split-K workspace and tickets (conv_tc.cu)
+    int* tc_tickets = nullptr;
     const float* amap_ws = nullptr;
     int amap_chunk = 0, amap_H = 0, amap_W = 0;
 };

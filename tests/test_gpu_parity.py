@@ -224,7 +224,7 @@ def nets(q):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
-@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 64, 40), (1, 224, 224), (9, 16, 24)])
+@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 64, 40), (1, 224, 224), (9, 16, 24), (3, 56, 120)])
 def test_denoiser_matches_cpu_forward(q, nets, shape, precision):
     """fp32 = CUDA-core exact mode; tc = tcgen05 split-bf16 tensor mode.  Same 1e-4 bar for both."""
     import torch
@@ -239,7 +239,7 @@ def test_denoiser_matches_cpu_forward(q, nets, shape, precision):
     try:
         out = net.forward(x.numpy())
     finally:
-        net.set_precision("fp32")
+        net.set_precision("tc")  # the library default
     assert out.shape == ref.shape
     err = rel_l2(out, ref)
     print(f"denoiser {precision} {shape}: rel-L2 {err:.3e}")
@@ -322,7 +322,7 @@ def test_admm_iter_counts_zero_and_one(q, ops):
         assert rel_l2(x, X0) <= 1e-6  # x_1 = X0 because A X0 = y (PnP_ADMM.m:102 with a zero residual)
 
 
-@pytest.mark.parametrize("dtype,precision", [("single_level", "fp32"), ("multi_level", "fp32"), ("single_level", "tc")])
+@pytest.mark.parametrize("dtype,precision", [("single_level", "fp32"), ("multi_level", "fp32"), ("single_level", "tc"), ("multi_level", "tc")])
 def test_admm_loop_with_builtin_unetres(q, ops, dtype, precision):
     """End to end: the on-device loop (K1 + K3) against the oracle loop with the CPU UNetRes."""
     from oracle import unetres
