@@ -55,6 +55,7 @@ struct TcConvParams {
     const void* mapA_lo[4];
     const void* mapB_hi;       // weights [N][K] K-major, box = tc_block_n(Cout) rows
     const void* mapB_lo;
+    const void* mapB_h2;       // pair kernel, stacked mode: w_hi with a box of Cout / 2 rows
 };
 
 int conv3x3_fp32(qmri_ctx* ctx, const ConvParams& p);
@@ -69,4 +70,7 @@ int tc_block_n(int Cout);
 size_t tc_partial_elems(int sm_count);
 size_t tc_ticket_count(int sm_count);
 int conv_tc(qmri_ctx* ctx, const TcConvParams& p);
+int tc_slab_tile_shape(int W, int H, int* BW, int* BH);
+void tc_pair_weight_boxes(int Cout, int* rows_main, int* rows_h2);
+int conv3x3_tc_pair(qmri_ctx* ctx, const TcConvParams& p);
 int normalize_planar(qmri_ctx* ctx, const float* in, float* out, const float* minmax, size_t per_slice, int S, int undo);

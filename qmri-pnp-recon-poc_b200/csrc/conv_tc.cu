@@ -40,7 +40,10 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <unistd.h>
 
 #include "common.cuh"
 #include "conv_kernels.h"
@@ -104,6 +107,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -112,6 +129,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 inputs, fp32 accumulate)
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -159,10 +181,19 @@ struct TcK {
     const uint16_t *res1_hi, *res1_lo, *res2_hi, *res2_lo;
     float* partial;
     int* tickets;
+    int* trace;  // QMRI_TC_TRACE: host-mapped progress words, 8 per CTA (debugging hangs of the warp-specialised roles)
     int S, H, W, Cin, Cout;
     int BW, BH, tiles_x, tiles_y;
     int relu, nsplit;
 };
+
+#define TC_TRACE(slot, val)                                                   \
+    do {                                                                      \
+        if (p.trace) {                                                        \
+            ((volatile int*)p.trace)[blockIdx.x * 8 + (slot)] = (int)(val);   \
+            __threadfence_system();                                           \
+        }                                                                     \
+    } while (0)
 
 // v[0..8) += hi + lo (8 bf16 pairs)
 __device__ __forceinline__ void add_split8(float* v, const uint4 a, const uint4 b) {
@@ -486,6 +517,371 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 conv, CTA-pair variant (tcgen05 cta_group::2) - the production path for the 58 3x3 convs.
+//
+// Measured with the single-CTA kernel above (profiles/): every MMA re-reads its A (4 KB) and B
+// (N x 32 B) operands from shared memory, and one SM feeds its tensor core at ~64 B/clk, so
+// M128 x N128 x K16 MMAs run at ~132 clk instead of 64 - half rate, whatever the L2 traffic (a
+// multicast / A-reuse variant with half the L2 traffic ran at exactly the same speed).  The fix
+// is the CTA pair: two CTAs (two SMs of a TPC) execute one M256 MMA; each supplies its own 128
+// pixel rows of A and HALF of the B columns, so per-SM operand traffic per flop halves.
+//
+// Work per pair: two pixel tiles (one per CTA) x one block of output channels.
+//   STACK = 0 (Cout >= 256): N = 256 output channels; three MMAs per K step
+//             (a_hi b_hi, a_hi b_lo, a_lo b_hi), CTA r holds weight rows [128 r, 128 r + 128) of both planes.
+//   STACK = 1 (Cout = NA/2 = 128 or 64): the hi and lo weight planes are stacked along N, B1 = [w_hi ; w_lo]:
+//             MMA 1 = a_hi x B1 (N = NA; CTA 0 holds w_hi, CTA 1 holds w_lo) leaves a_hi w_hi in
+//             accumulator columns [0, Cout) and a_hi w_lo in [Cout, 2 Cout); MMA 2 = a_lo x w_hi (N = Cout)
+//             adds into [0, Cout); the epilogue sums the two column blocks.  Two MMAs instead of three.
+// A operand: "slab" reuse - for every (64-channel block, dx) the (BH + 2) x BW pixel slab shifted by dx is
+// loaded once; BW is a multiple of 8 pixels (8 x 128 B = one swizzle atom), so the A operand of tap dy is
+// the same slab (dy + 1) * BW rows further, still 1024-byte aligned (descriptors that start inside a
+// swizzle atom were measured ~2x slower).
+// Barriers: full (TMA -> MMA) and tempty (epilogue -> MMA) live in the leader CTA, the peer's TMA and
+// epilogue warps signal them remotely; empty / tfull are per CTA and are signalled by multicast commits.
+// ------------------------------------------------------------------------------------------------
+template <int NA, int STACK>
+struct PairCfg {
+    static constexpr int NOUT = STACK ? NA / 2 : NA;             // output channels per tile
+    static constexpr uint32_t A_PLANE = 20480;                   // (8 + 2) x 16 rows of 128 B: the larger of the two tile shapes
+    static constexpr uint32_t A_SLOT = 2 * A_PLANE;              // hi + lo
+    static constexpr uint32_t B1_BYTES = (NA / 2) * 128;         // this CTA's half of the N = NA operand
+    static constexpr uint32_t B2_BYTES = STACK ? (NA / 4) * 128 : B1_BYTES;  // STACK: half of the N = NA/2 operand; else the lo plane
+    static constexpr uint32_t B_STAGE = B1_BYTES + B2_BYTES;
+    static constexpr int AS = (NA == 128) ? 3 : 2;
+    static constexpr int BS = (NA == 128) ? 8 : (STACK ? 5 : 4);
+    static constexpr uint32_t TMEM_COLS = 2 * NA;                // two accumulators
+    static constexpr size_t SMEM = (size_t)AS * A_SLOT + (size_t)BS * B_STAGE + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile loads of a CTA pair: data lands in this CTA, completion is signalled on `bar_cluster_addr` (the leader's barrier)
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint64_t* bar) {  // arrive on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// 16 consecutive output channels of this thread's pixel from the accumulator (STACK: sum of the two column blocks)
+template <int NA, int STACK>
+__device__ __forceinline__ void pair_acc16(uint32_t taddr, int c0, float* v) {
+    uint32_t a[16];
+    tc_ld16(taddr + c0, a);
+    if (STACK) {
+        uint32_t b[16];
+        tc_ld16(taddr + NA / 2 + c0, b);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+    } else {
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]);
+    }
+}
+
+template <int NA, int STACK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                       const __grid_constant__ CUtensorMap tmB_h2, const TcK p) {
+    using Cfg = PairCfg<NA, STACK>;
+    constexpr int AS = Cfg::AS, BS = Cfg::BS, NOUT = Cfg::NOUT;
+    extern __shared__ unsigned char tc_smem_raw[];
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    unsigned char* smemB = smem + (size_t)AS * Cfg::A_SLOT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)BS * Cfg::B_STAGE);
+    uint64_t* fullA = bars;               // leader's are used
+    uint64_t* emptyA = bars + AS;         // per CTA
+    uint64_t* fullB = bars + 2 * AS;      // leader's
+    uint64_t* emptyB = bars + 2 * AS + BS;
+    uint64_t* tfull = bars + 2 * AS + 2 * BS;  // per CTA
+    uint64_t* tempty = tfull + 2;              // leader's
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cblocks = p.Cin / TC_BK;
+    const int U = 3 * cblocks;                                // K units: (channel block, dx); each = 1 slab + 3 weight tiles
+    const int NT = p.Cout / NOUT;
+    const int tiles_xy = p.tiles_x * p.tiles_y;
+    const int ptiles = tiles_xy * p.S;                        // pixel tiles
+    const int pgroups = (ptiles + 1) / 2;
+    const int total_work = pgroups * NT * p.nsplit;           // per pair: (pixel-tile pair, channel block, K split)
+    const int crank = (int)cluster_ctarank();
+    const int cidx = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const uint32_t slab_bytes = (uint32_t)((p.BH + 2) * p.BW * 128);
+    const uint32_t dy_bytes = (uint32_t)(p.BW * 128);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < AS; ++s) {
+            mbar_init(&fullA[s], 1);
+            mbar_init(&emptyA[s], 1);
+        }
+        for (int s = 0; s < BS; ++s) {
+            mbar_init(&fullB[s], 1);
+            mbar_init(&emptyB[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 8);  // 4 epilogue warps of each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&tmA_hi);
+        tma_prefetch_desc(&tmA_lo);
+        tma_prefetch_desc(&tmB_hi);
+        tma_prefetch_desc(&tmB_lo);
+        tma_prefetch_desc(&tmB_h2);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(7, -1);
+    cluster_sync_all();  // both CTAs' barriers are initialised and TMEM is allocated before any cross-CTA signal
+    if (threadIdx.x == 0) TC_TRACE(7, -2);
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int w = cidx; w < total_work; w += nclusters) {
+                const int split = w % p.nsplit;
+                const int r = w / p.nsplit;
+                const int nt = r % NT;
+                const int pt = (r / NT) * 2 + crank;
+                // a rank past the last pixel tile still supplies its half of the weights; its slab is all out of bounds (zeros)
+                const int txy = pt % tiles_xy;
+                const int s = (pt < ptiles) ? pt / tiles_xy : p.S;
+                const int x0 = (txy % p.tiles_x) * p.BW, y0 = (txy / p.tiles_x) * p.BH;
+                const int u0 = (split * U) / p.nsplit, u1 = ((split + 1) * U) / p.nsplit;
+                for (int u = u0; u < u1; ++u) {
+                    const int cb = u / 3, dxi = u - 3 * cb;
+                    TC_TRACE(0, (w << 12) | (u << 4) | 1);
+                    mbar_wait(&emptyA[sa], pa ^ 1);
+                    unsigned char* st = smem + (size_t)sa * Cfg::A_SLOT;
+                    if (crank == 0) mbar_expect_tx(&fullA[sa], 4 * slab_bytes);  // both CTAs' hi + lo slabs
+                    const uint32_t barA = mapa_rank(smem_u32(&fullA[sa]), 0);
+                    tma2_load_4d(st, &tmA_hi, barA, cb * TC_BK, x0 + dxi - 1, y0 - 1, s);
+                    tma2_load_4d(st + Cfg::A_PLANE, &tmA_lo, barA, cb * TC_BK, x0 + dxi - 1, y0 - 1, s);
+                    if (++sa == AS) {
+                        sa = 0;
+                        pa ^= 1;
+                    }
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        const int kcol = (dyi * 3 + dxi) * p.Cin + cb * TC_BK;
+                        TC_TRACE(0, (w << 12) | (u << 4) | (2 + dyi));
+                        mbar_wait(&emptyB[sb], pb ^ 1);
+                        unsigned char* sbp = smemB + (size_t)sb * Cfg::B_STAGE;
+                        if (crank == 0) mbar_expect_tx(&fullB[sb], 2 * Cfg::B_STAGE);
+                        const uint32_t barB = mapa_rank(smem_u32(&fullB[sb]), 0);
+                        if (STACK) {
+                            // B1 = [w_hi ; w_lo] (N = NA): CTA 0 holds the hi plane, CTA 1 the lo plane; B2 = w_hi (N = NOUT), split by rows
+                            tma2_load_2d(sbp, crank == 0 ? &tmB_hi : &tmB_lo, barB, kcol, 0);
+                            tma2_load_2d(sbp + Cfg::B1_BYTES, &tmB_h2, barB, kcol, crank * (NOUT / 2));
+                        } else {
+                            tma2_load_2d(sbp, &tmB_hi, barB, kcol, nt * NOUT + crank * (NA / 2));
+                            tma2_load_2d(sbp + Cfg::B1_BYTES, &tmB_lo, barB, kcol, nt * NOUT + crank * (NA / 2));
+                        }
+                        if (++sb == BS) {
+                            sb = 0;
+                            pb ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (lane == 0 && crank == 0) {
+            // instruction descriptors: D = f32, A = B = bf16, K-major, M = 256
+            const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t idesc_full = idesc_base | ((uint32_t)(NA >> 3) << 17);
+            const uint32_t idesc_half = idesc_base | ((uint32_t)((NA / 2) >> 3) << 17);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int w = cidx; w < total_work; w += nclusters, ++it) {
+                const int split = w % p.nsplit;
+                const int u0 = (split * U) / p.nsplit, u1 = ((split + 1) * U) / p.nsplit;
+                const int ab = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                TC_TRACE(1, (w << 12) | 0xF00);
+                mbar_wait(&tempty[ab], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(ab * NA);
+                for (int u = u0; u < u1; ++u) {
+                    TC_TRACE(1, (w << 12) | (u << 4) | 1);
+                    mbar_wait(&fullA[sa], pa);
+                    tc_fence_after();
+                    const uint32_t ha = smem_u32(smem + (size_t)sa * Cfg::A_SLOT);
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        TC_TRACE(1, (w << 12) | (u << 4) | (2 + dyi));
+                        mbar_wait(&fullB[sb], pb);
+                        tc_fence_after();
+                        const uint32_t sbase = smem_u32(smemB + (size_t)sb * Cfg::B_STAGE);
+                        const uint64_t a_hi = umma_desc(ha + dyi * dy_bytes), a_lo = umma_desc(ha + Cfg::A_PLANE + dyi * dy_bytes);
+                        const uint64_t b_1 = umma_desc(sbase), b_2 = umma_desc(sbase + Cfg::B1_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            const uint32_t acc = ((u - u0) | dyi | k) ? 1u : 0u;
+                            if (STACK) {
+                                tc2_mma(tmem_d, a_hi + ko, b_1 + ko, idesc_full, acc);   // [a_hi w_hi | a_hi w_lo]
+                                tc2_mma(tmem_d, a_lo + ko, b_2 + ko, idesc_half, 1u);    // += a_lo w_hi into the first block
+                            } else {
+                                tc2_mma(tmem_d, a_hi + ko, b_1 + ko, idesc_full, acc);
+                                tc2_mma(tmem_d, a_hi + ko, b_2 + ko, idesc_full, 1u);
+                                tc2_mma(tmem_d, a_lo + ko, b_1 + ko, idesc_full, 1u);
+                            }
+                        }
+                        tc2_commit(&emptyB[sb]);  // frees the stage in both CTAs
+                        if (++sb == BS) {
+                            sb = 0;
+                            pb ^= 1;
+                        }
+                    }
+                    tc2_commit(&emptyA[sa]);
+                    if (++sa == AS) {
+                        sa = 0;
+                        pa ^= 1;
+                    }
+                }
+                tc2_commit(&tfull[ab]);  // accumulator complete: wakes the epilogue warps of both CTAs
+            }
+        }
+    } else {
+        // ================= epilogue warps (both CTAs; each drains its own 128 accumulator rows) =================
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        int it = 0;
+        for (int w = cidx; w < total_work; w += nclusters, ++it) {
+            const int split = w % p.nsplit;
+            const int r = w / p.nsplit;
+            const int ab = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int nt = r % NT;
+            const int pt = (r / NT) * 2 + crank;
+            const bool live = pt < ptiles;
+            const int txy = pt % tiles_xy;
+            const int s = pt / tiles_xy;
+            const int x = (txy % p.tiles_x) * p.BW + row % p.BW;
+            const int y = (txy / p.tiles_x) * p.BH + row / p.BW;
+            const bool ok = live && (x < p.W) && (y < p.H);
+            const size_t o = (((size_t)s * p.H + y) * p.W + x) * p.Cout + (size_t)nt * NOUT;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * NA);
+            const uint32_t tempty_leader = mapa_rank(smem_u32(&tempty[ab]), 0);
+            if (lane == 0) TC_TRACE(2 + lg, (w << 12) | 1);
+            mbar_wait(&tfull[ab], aphase);
+            tc_fence_after();
+            if (lane == 0) TC_TRACE(2 + lg, (w << 12) | 2);
+            if (p.nsplit == 1) {
+                // tcgen05.ld is .sync.aligned: every lane of the warp executes it, only the memory accesses depend on `ok`
+                const bool has_r1 = ok && (p.res1_hi != nullptr), has_r2 = ok && (p.res2_hi != nullptr);
+#pragma unroll 1
+                for (int cc = 0; cc < NOUT; cc += 16) {
+                    float v[16];
+                    uint4 r1[4], r2[4];
+                    if (has_r1) {  // issue the residual loads before the TMEM read
+                        const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o + cc);
+                        const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o + cc);
+                        r1[0] = gh[0]; r1[1] = gh[1]; r1[2] = gl[0]; r1[3] = gl[1];
+                    }
+                    if (has_r2) {
+                        const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o + cc);
+                        const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o + cc);
+                        r2[0] = gh[0]; r2[1] = gh[1]; r2[2] = gl[0]; r2[3] = gl[1];
+                    }
+                    pair_acc16<NA, STACK>(taddr, cc, v);
+                    if (has_r1) {
+                        add_split8(v, r1[0], r1[2]);
+                        add_split8(v + 8, r1[1], r1[3]);
+                    }
+                    if (has_r2) {
+                        add_split8(v, r2[0], r2[2]);
+                        add_split8(v + 8, r2[1], r2[3]);
+                    }
+                    if (ok) store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader);
+            } else {
+                const int t = pt * NT + nt;
+                float* prow0 = p.partial + ((size_t)t * p.nsplit * TC_BM + row) * NOUT;
+                if (live) {
+                    float* prow = prow0 + (size_t)split * TC_BM * NOUT;
+#pragma unroll 1
+                    for (int cc = 0; cc < NOUT; cc += 16) {
+                        float v[16];
+                        pair_acc16<NA, STACK>(taddr, cc, v);
+                        float4* d = reinterpret_cast<float4*>(prow + cc);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader);
+                if (live) {
+                    __threadfence();
+                    __syncwarp();
+                    int old = 0;
+                    if (lane == 0) old = atomicAdd(&p.tickets[t * 4 + lg], 1);
+                    old = __shfl_sync(0xffffffffu, old, 0);
+                    if (old == p.nsplit - 1) {
+                        __threadfence();
+                        if (lane == 0) p.tickets[t * 4 + lg] = 0;
+                        if (ok) tc_epilogue_reduce<NOUT>(p, prow0, o);
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) TC_TRACE(6, 0x1000 + warp);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(7, 1);
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal its barriers or run MMAs on it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS));
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -564,7 +960,7 @@ int tc_tile_shape(int W, int H, int* BW, int* BH) {
 
 int tc_block_n(int Cout) { return Cout == 64 ? 64 : 128; }
 
-size_t tc_partial_elems(int sm_count) { return (size_t)sm_count * TC_BM * 128; }
+size_t tc_partial_elems(int sm_count) { return (size_t)sm_count * TC_BM * 256; }
 size_t tc_ticket_count(int sm_count) { return (size_t)sm_count * 4; }
 
 template <int BN, int MODE>
@@ -615,7 +1011,7 @@ int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
     k.partial = p.partial; k.tickets = p.tickets;
     k.S = p.S; k.H = p.H; k.W = p.W; k.Cin = p.Cin; k.Cout = p.Cout;
     k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
-    k.relu = p.relu; k.nsplit = nsplit;
+    k.relu = p.relu; k.nsplit = nsplit; k.trace = nullptr;
     if (BN == 64) {
         if (p.mode == TC_CONV3X3) return launch_tc<64, 0>(ctx, maps, k, grid);
         if (p.mode == TC_DOWN2X2) return launch_tc<64, 1>(ctx, maps, k, grid);
@@ -624,4 +1020,122 @@ int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
     if (p.mode == TC_CONV3X3) return launch_tc<128, 0>(ctx, maps, k, grid);
     if (p.mode == TC_DOWN2X2) return launch_tc<128, 1>(ctx, maps, k, grid);
     return launch_tc<128, 2>(ctx, maps, k, grid);
+}
+
+// pair kernel: BW must be a multiple of 8 pixels (dy shifts stay 1024-byte aligned)
+int tc_slab_tile_shape(int W, int H, int* BW, int* BH) {
+    const int cand[2][2] = {{16, 8}, {8, 16}};
+    int best = 0;
+    double best_eff = -1;
+    for (int i = 0; i < 2; ++i) {
+        int bw = cand[i][0], bh = cand[i][1];
+        double eff = ((double)W * H) / ((double)((W + bw - 1) / bw * bw) * ((H + bh - 1) / bh * bh));
+        if (i == 1) eff *= 1.04;  // the 8 x 16 slab is 10 % smaller; prefer it on ties
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = i;
+        }
+    }
+    *BW = cand[best][0];
+    *BH = cand[best][1];
+    return QMRI_OK;
+}
+
+// weight-map box rows the pair kernel expects for a 3x3 conv with Cout output channels:
+// rows[0] for mapB_hi / mapB_lo, rows[1] for the third map (second half-width copy of w_hi; stacked mode only)
+void tc_pair_weight_boxes(int Cout, int* rows_main, int* rows_h2) {
+    if (Cout >= 256) {
+        *rows_main = 128;
+        *rows_h2 = 128;  // unused
+    } else {
+        *rows_main = Cout;
+        *rows_h2 = Cout / 2;
+    }
+}
+
+template <int NA, int STACK>
+static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
+    using Cfg = PairCfg<NA, STACK>;
+    static bool configured = false;
+    if (!configured) {
+        QCUDA(cudaFuncSetAttribute(tc_conv3x3_pair_kernel<NA, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int ptiles = p.tiles_x * p.tiles_y * p.S;
+    const int NT = p.Cout / Cfg::NOUT;
+    const int groups = ((ptiles + 1) / 2) * NT;
+    const int max_clusters = ctx->sm_count / 2;
+    const int U = 3 * (p.Cin / TC_BK);
+    int nsplit = 1;
+    if (p.partial && p.tickets && 2 * groups <= max_clusters) {
+        nsplit = max_clusters / groups;
+        if (nsplit > U / 2) nsplit = U / 2;
+        if (nsplit > 8) nsplit = 8;
+        if (nsplit < 1) nsplit = 1;
+    }
+    k.nsplit = nsplit;
+    const int work = groups * nsplit;
+    const int nclusters = work < max_clusters ? work : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nclusters * 2);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int* trace_host = nullptr;
+    static int* trace_dev = nullptr;
+    static const bool trace_on = getenv("QMRI_TC_TRACE") != nullptr;
+    if (trace_on && !trace_host) {
+        QCUDA(cudaHostAlloc((void**)&trace_host, 256 * 8 * sizeof(int), cudaHostAllocMapped));
+        QCUDA(cudaHostGetDevicePointer((void**)&trace_dev, trace_host, 0));
+    }
+    if (trace_on) {
+        memset(trace_host, 0, 256 * 8 * sizeof(int));
+        k.trace = trace_dev;
+    }
+    QCUDA(cudaLaunchKernelEx(&cfg, tc_conv3x3_pair_kernel<NA, STACK>, *(const CUtensorMap*)p.mapA_hi[0], *(const CUtensorMap*)p.mapA_lo[0],
+                             *(const CUtensorMap*)p.mapB_hi, *(const CUtensorMap*)p.mapB_lo, *(const CUtensorMap*)p.mapB_h2, (const TcK)k));
+    QLAUNCH_CHECK(ctx);
+    if (trace_on) {  // watchdog: a hang dumps where every role of every CTA stopped, then the process exits
+        for (int ms = 0; ms < 5000; ++ms) {
+            if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady) return QMRI_OK;
+            struct timespec ts = {0, 1000000};
+            nanosleep(&ts, nullptr);
+        }
+        fprintf(stderr, "[qmri trace] pair kernel NA=%d STACK=%d hung: S=%d H=%d W=%d Cin=%d Cout=%d tile %dx%d nsplit=%d clusters=%d work=%d\n", NA, STACK,
+                p.S, p.H, p.W, p.Cin, p.Cout, p.BW, p.BH, nsplit, nclusters, work);
+        for (int c = 0; c < nclusters * 2; ++c) {
+            const int* t = trace_host + c * 8;
+            fprintf(stderr, "[qmri trace] cta %3d prod %08x mma %08x epi %08x %08x %08x %08x end %08x sync %d\n", c, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+        }
+        _exit(3);
+    }
+    return QMRI_OK;
+}
+
+// 3x3 conv through the CTA-pair kernel.  mapA_*[0]: activation maps with box (BW, BH + 2); mapB_hi / mapB_lo / mapB_h2:
+// weight maps with the box rows of tc_pair_weight_boxes().
+int conv3x3_tc_pair(qmri_ctx* ctx, const TcConvParams& p) {
+    if (p.Cin % TC_BK) return qmri_fail(QMRI_EINVAL, "conv3x3_tc_pair: Cin %% 64");
+    if (p.Cout != 64 && p.Cout != 128 && p.Cout % 256) return qmri_fail(QMRI_EINVAL, "conv3x3_tc_pair: Cout %d", p.Cout);
+    if (p.BW % 8 || p.BW * p.BH != TC_BM || (p.BH + 2) * p.BW * 128 > (int)PairCfg<256, 0>::A_PLANE)
+        return qmri_fail(QMRI_EINVAL, "conv3x3_tc_pair: tile %d x %d not supported", p.BW, p.BH);
+    if (!p.mapA_hi[0] || !p.mapA_lo[0] || !p.mapB_hi || !p.mapB_lo || !p.mapB_h2) return qmri_fail(QMRI_EINVAL, "conv3x3_tc_pair: missing tensor map");
+    TcK k;
+    k.out_hi = p.out_hi; k.out_lo = p.out_lo;
+    k.res1_hi = p.res1_hi; k.res1_lo = p.res1_lo;
+    k.res2_hi = p.res2_hi; k.res2_lo = p.res2_lo;
+    k.partial = p.partial; k.tickets = p.tickets;
+    k.S = p.S; k.H = p.H; k.W = p.W; k.Cin = p.Cin; k.Cout = p.Cout;
+    k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
+    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr;
+    if (p.Cout == 64) return launch_pair<128, 1>(ctx, p, k);
+    if (p.Cout == 128) return launch_pair<256, 1>(ctx, p, k);
+    return launch_pair<256, 0>(ctx, p, k);
 }

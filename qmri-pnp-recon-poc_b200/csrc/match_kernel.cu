@@ -7,11 +7,15 @@
 //
 // FP32-FMA pipe: every thread keeps PX pixels' C-channel complex signatures in registers
 // (2*C*PX floats); atoms are staged through shared memory in chunks and read as warp-wide
-// broadcasts (LDS.128), so per (pixel, atom) the SM issues 2*C FFMA + 2 for |.|^2 + a compare/
-// select.  The running best is carried as a packed 64-bit key
+// broadcasts (LDS.128).  Per (pixel, atom) the SM issues 2*C FFMA + FMUL + FFMA for |.|^2 and ONE
+// FMNMX: only the running maximum of a group of 16 atoms is tracked in the inner loop, the
+// (max, group) compare/select happens once per group, and the winning group is rescanned at the end
+// with bit-identical arithmetic to recover the first atom attaining the maximum (MATLAB's
+// first-index tie rule: strict > across groups keeps the first group, the rescan the first atom).
+// The result is carried as a packed 64-bit key
 //     key = float_bits(score^2) << 32 | (0xFFFFFFFF - atom_index)
-// whose integer max is "largest score, lowest index on ties" = MATLAB's first-index rule; the
-// same key is what atom-sharded ranks reduce with an integer max (qmri.h, BASELINE config 5).
+// whose integer max is "largest score, lowest index on ties"; the same key is what atom-sharded
+// ranks reduce with an integer max (qmri.h, BASELINE config 5).
 #include <math.h>
 #include <string.h>
 
@@ -22,6 +26,19 @@ namespace {
 
 constexpr int K2_THREADS = 256;
 constexpr int K2_CHUNK = 512;  // atoms per shared-memory stage
+constexpr int K2_GROUP = 16;   // atoms per (max, index) bookkeeping step
+
+// |<d, x>|^2 with a fixed operation order (the rescan must reproduce the main loop bit for bit)
+template <int C, bool CPLX>
+__device__ __forceinline__ float k2_score(const float* d, const float* xr, const float* xi) {
+    float sr = 0.f, si = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        sr = fmaf(d[c], xr[c], sr);
+        if (CPLX) si = fmaf(d[c], xi[c], si);
+    }
+    return CPLX ? fmaf(si, si, sr * sr) : sr * sr;
+}
 
 template <int C, int CP, int PX, bool CPLX>
 __global__ void __launch_bounds__(K2_THREADS) match_kernel(K2Params p) {
@@ -33,7 +50,7 @@ __global__ void __launch_bounds__(K2_THREADS) match_kernel(K2Params p) {
     const int64_t ka = p.a0 + (int64_t)blockIdx.y * per;
     const int64_t kb = min(p.a1, ka + per);
 
-    float xr[PX][C], xi[PX][C];
+    float xr[PX][C], xi[PX][CPLX ? C : 1];
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         int64_t pix = pix0 + tid + (int64_t)i * K2_THREADS;
@@ -41,62 +58,84 @@ __global__ void __launch_bounds__(K2_THREADS) match_kernel(K2Params p) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             xr[i][c] = (ok && c < p.C) ? __ldg(p.x_re + (int64_t)c * p.npix + pix) : 0.f;
-            xi[i][c] = (CPLX && ok && c < p.C) ? __ldg(p.x_im + (int64_t)c * p.npix + pix) : 0.f;
+            if (CPLX) xi[i][c] = (ok && c < p.C) ? __ldg(p.x_im + (int64_t)c * p.npix + pix) : 0.f;
         }
     }
     float best[PX];
-    int bidx[PX];
+    int bgrp[PX];  // winning group, counted from ka in units of K2_GROUP atoms
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         best[i] = -1.f;
-        bidx[i] = 0;
+        bgrp[i] = 0;
     }
 
     for (int64_t k0 = ka; k0 < kb; k0 += K2_CHUNK) {
         const int nk = (int)min((int64_t)K2_CHUNK, kb - k0);
+        const int ngrp = (nk + K2_GROUP - 1) / K2_GROUP;
         __syncthreads();
         {
             const float4* src = reinterpret_cast<const float4*>(p.Dp + k0 * CP);
             float4* dst = reinterpret_cast<float4*>(atoms);
-            const int n4 = nk * CP / 4;
-            for (int i = tid; i < n4; i += K2_THREADS) dst[i] = __ldg(src + i);
+            const int n4 = nk * CP / 4, n4pad = ngrp * K2_GROUP * CP / 4;
+            // atoms past the range are zero: their score 0 can never be strictly greater than a real score
+            for (int i = tid; i < n4pad; i += K2_THREADS) dst[i] = (i < n4) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
-#pragma unroll 2
-        for (int a = 0; a < nk; ++a) {
+        const int g0 = (int)((k0 - ka) / K2_GROUP);
+#pragma unroll 1
+        for (int g = 0; g < ngrp; ++g) {
+            float gmax[PX];
+#pragma unroll
+            for (int i = 0; i < PX; ++i) gmax[i] = -1.f;
+#pragma unroll 4
+            for (int a = 0; a < K2_GROUP; ++a) {
+                float d[CP];
+#pragma unroll
+                for (int q = 0; q < CP / 4; ++q) {
+                    float4 t = *reinterpret_cast<const float4*>(atoms + (g * K2_GROUP + a) * CP + 4 * q);
+                    d[4 * q] = t.x;
+                    d[4 * q + 1] = t.y;
+                    d[4 * q + 2] = t.z;
+                    d[4 * q + 3] = t.w;
+                }
+#pragma unroll
+                for (int i = 0; i < PX; ++i) gmax[i] = fmaxf(gmax[i], k2_score<C, CPLX>(d, xr[i], xi[i]));  // fmaxf drops NaN
+            }
+#pragma unroll
+            for (int i = 0; i < PX; ++i)
+                if (gmax[i] > best[i]) {  // strict: the first group wins ties
+                    best[i] = gmax[i];
+                    bgrp[i] = g0 + g;
+                }
+        }
+    }
+    // rescan the winning group: first atom whose score equals the maximum
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        int64_t pix = pix0 + tid + (int64_t)i * K2_THREADS;
+        if (pix >= p.npix || !(best[i] >= 0.f)) continue;
+        const int64_t kg = ka + (int64_t)bgrp[i] * K2_GROUP;
+        int64_t win = kg;
+        bool found = false;
+        for (int a = 0; a < K2_GROUP; ++a) {
+            const int64_t k = kg + a;
+            if (k >= kb || found) break;
             float d[CP];
 #pragma unroll
             for (int q = 0; q < CP / 4; ++q) {
-                float4 t = *reinterpret_cast<const float4*>(atoms + a * CP + 4 * q);
+                float4 t = __ldg(reinterpret_cast<const float4*>(p.Dp + k * CP + 4 * q));
                 d[4 * q] = t.x;
                 d[4 * q + 1] = t.y;
                 d[4 * q + 2] = t.z;
                 d[4 * q + 3] = t.w;
             }
-#pragma unroll
-            for (int i = 0; i < PX; ++i) {
-                float sr = 0.f, si = 0.f;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    sr = fmaf(d[c], xr[i][c], sr);
-                    if (CPLX) si = fmaf(d[c], xi[i][c], si);
-                }
-                float sc = CPLX ? fmaf(si, si, sr * sr) : sr * sr;
-                if (sc > best[i]) {  // strict: the first (lowest) index wins ties
-                    best[i] = sc;
-                    bidx[i] = (int)(k0 - p.a0) + a;
-                }
+            if (k2_score<C, CPLX>(d, xr[i], xi[i]) == best[i]) {
+                win = k;
+                found = true;
             }
         }
-    }
-#pragma unroll
-    for (int i = 0; i < PX; ++i) {
-        int64_t pix = pix0 + tid + (int64_t)i * K2_THREADS;
-        if (pix < p.npix && best[i] >= 0.f) {
-            unsigned long long key = ((unsigned long long)__float_as_uint(best[i]) << 32) |
-                                     (unsigned long long)(0xFFFFFFFFu - (unsigned)(p.a0 + bidx[i]));
-            atomicMax(p.keys + pix, key);
-        }
+        unsigned long long key = ((unsigned long long)__float_as_uint(best[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)win);
+        atomicMax(p.keys + pix, key);
     }
 }
 
@@ -130,14 +169,30 @@ __global__ void match_finish_kernel(K2Finish p) {
 
 template <int C, int CP>
 int launch_c(qmri_ctx* ctx, const K2Params& p) {
-    constexpr int PX = 2;
+    constexpr int PX = 4;
     const int64_t ppb = (int64_t)K2_THREADS * PX;
     int64_t gx = (p.npix + ppb - 1) / ppb;
-    // split the atom range so that small pixel counts still fill the machine (>= 2 waves)
+    // split the atom range so that the grid fills whole waves of resident CTAs (small pixel counts would
+    // otherwise leave SMs idle or end with a mostly empty last wave)
+    static int per_sm = 0;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<C, CP, PX, true>, K2_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const int64_t slots = (int64_t)ctx->sm_count * per_sm;
     int64_t natoms = p.a1 - p.a0;
-    int64_t want = (2LL * ctx->sm_count * 2 + gx - 1) / gx;  // 2 CTAs/SM resident
-    int64_t maxsplit = std::max<int64_t>(1, natoms / (4 * K2_CHUNK));
-    int gy = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, maxsplit), 65535));
+    int64_t maxsplit = std::max<int64_t>(1, std::min<int64_t>(natoms / (2 * K2_CHUNK), 4096));
+    int gy = 1;
+    double best_eff = 0.0;
+    for (int64_t cand = 1; cand <= maxsplit; ++cand) {
+        const int64_t ctas = gx * cand;
+        const int64_t waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / (double)(waves * slots);
+        if (eff > best_eff + 0.02) {  // prefer fewer splits unless clearly better
+            best_eff = eff;
+            gy = (int)cand;
+        }
+        if (waves >= 8) break;
+    }
     dim3 grid((unsigned)gx, (unsigned)gy);
     if (p.x_im) match_kernel<C, CP, PX, true><<<grid, K2_THREADS, 0, ctx->stream>>>(p);
     else match_kernel<C, CP, PX, false><<<grid, K2_THREADS, 0, ctx->stream>>>(p);

@@ -137,6 +137,7 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
     qmri_net* net = new qmri_net();
     net->ctx = ctx;
     net->in_nc = in_nc;
+    if (const char* e = getenv("QMRI_TC_PAIR")) net->tc_pair = atoi(e);  // A/B timing experiments: bit l = U-Net level l uses the pair kernel
     auto L = layer_table(in_nc);
     std::vector<float> packed;
     for (int o = 0; o < 2; ++o) {
@@ -163,6 +164,9 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
         net->wtc_lo[o].assign(64, nullptr);
         net->wmap_hi[o].resize(64);
         net->wmap_lo[o].resize(64);
+        net->wmapp_hi[o].resize(64);
+        net->wmapp_lo[o].resize(64);
+        net->wmapp_h2[o].resize(64);
         std::vector<uint16_t> hi, lo;
         for (int l = 0; l < 64 && net->tc_available; ++l) {
             if (L[l].kind > 2) continue;
@@ -179,6 +183,13 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
             const int N = (L[l].kind == 2 ? 4 : 1) * L[l].cout;
             r = tc_make_weight_map(&net->wmap_hi[o][l], net->wtc_hi[o][l], K, N, BN) |
                 tc_make_weight_map(&net->wmap_lo[o][l], net->wtc_lo[o][l], K, N, BN);
+            if (!r && L[l].kind == 0) {
+                int rows_main, rows_h2;
+                tc_pair_weight_boxes(L[l].cout, &rows_main, &rows_h2);
+                r = tc_make_weight_map(&net->wmapp_hi[o][l], net->wtc_hi[o][l], K, N, rows_main) |
+                    tc_make_weight_map(&net->wmapp_lo[o][l], net->wtc_lo[o][l], K, N, rows_main) |
+                    tc_make_weight_map(&net->wmapp_h2[o][l], net->wtc_hi[o][l], K, N, rows_h2);
+            }
             if (r) net->tc_available = false;  // driver entry point missing: tensor mode off, exact fp32 mode still works
         }
     }
@@ -332,6 +343,10 @@ static int build_act_maps(qmri_net* net, int H, int W) {
         for (int b = 0; b < 3; ++b) {
             QCHECK(tc_make_act_map(&net->amap[b][l][0], hi[b][l], net->chunk, H >> l, W >> l, NC[l], BW, BH));
             QCHECK(tc_make_act_map(&net->amap[b][l][1], lo[b][l], net->chunk, H >> l, W >> l, NC[l], BW, BH));
+            int SW, SH;
+            tc_slab_tile_shape(W >> l, H >> l, &SW, &SH);
+            QCHECK(tc_make_act_map(&net->amap_slab[b][l][0], hi[b][l], net->chunk, H >> l, W >> l, NC[l], SW, SH + 2));
+            QCHECK(tc_make_act_map(&net->amap_slab[b][l][1], lo[b][l], net->chunk, H >> l, W >> l, NC[l], SW, SH + 2));
             if (l < 3) {  // stride-2 tap views feeding the down conv to level l + 1
                 int DW, DH;
                 tc_tile_shape(W >> (l + 1), H >> (l + 1), &DW, &DH);
@@ -419,6 +434,15 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
         p.S = S; p.H = H >> lvl; p.W = W >> lvl; p.Cin = NC[lvl]; p.Cout = NC[lvl];
         p.relu = relu;
         tiles(p);
+        if ((net->tc_pair >> lvl) & 1) {
+            tc_slab_tile_shape(p.W, p.H, &p.BW, &p.BH);
+            p.tiles_x = (p.W + p.BW - 1) / p.BW;
+            p.tiles_y = (p.H + p.BH - 1) / p.BH;
+            p.mapA_hi[0] = &net->amap_slab[src][lvl][0]; p.mapA_lo[0] = &net->amap_slab[src][lvl][1];
+            p.mapB_hi = &net->wmapp_hi[orient][layer]; p.mapB_lo = &net->wmapp_lo[orient][layer];
+            p.mapB_h2 = &net->wmapp_h2[orient][layer];
+            return conv3x3_tc_pair(ctx, p);
+        }
         p.mapA_hi[0] = &net->amap[src][lvl][0]; p.mapA_lo[0] = &net->amap[src][lvl][1];
         p.mapB_hi = &net->wmap_hi[orient][layer]; p.mapB_lo = &net->wmap_lo[orient][layer];
         return conv_tc(ctx, p);

@@ -29,6 +29,9 @@ struct qmri_net {
     std::vector<TMap> wmap_hi[2], wmap_lo[2];
     // activation TMA maps per workspace buffer (X, A, T) x level x plane (hi, lo); rebuilt when the workspace moves
     TMap amap[3][4][2];
+    TMap amap_slab[3][4][2];     // (BH + 2) x BW slabs for the CTA-pair 3x3 kernel
+    std::vector<TMap> wmapp_hi[2], wmapp_lo[2], wmapp_h2[2];  // 3x3 weights with the box rows of the CTA-pair kernel
+    int tc_pair = 15;            // 3x3 convs, bit l = level l: 1 = CTA-pair kernel (cta_group::2, slab A reuse), 0 = single-CTA per-tap kernel
     TMap amap_down[3][3][4][2];  // buffer x input level x tap (dy*2+dx) x plane: stride-2 views for the 2x2 s2 convs
     float* tc_partial = nullptr; // split-K workspace and tickets (conv_tc.cu)
     int* tc_tickets = nullptr;
