@@ -805,41 +805,52 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * NA);
             const uint32_t tempty_leader = mapa_rank(smem_u32(&tempty[ab]), 0);
             if (lane == 0) TC_TRACE(2 + lg, (w << 12) | 1);
-            mbar_wait(&tfull[ab], aphase);
-            tc_fence_after();
-            if (lane == 0) TC_TRACE(2 + lg, (w << 12) | 2);
             if (p.nsplit == 1) {
-                // tcgen05.ld is .sync.aligned: every lane of the warp executes it, only the memory accesses depend on `ok`
+                // The ResBlock residual of this pixel is fetched into registers BEFORE waiting for the accumulator (up to 128
+                // channels at a time), so its latency hides behind the tile's MMA main loop.  tcgen05.ld is .sync.aligned:
+                // every lane of the warp executes it, only the memory accesses depend on `ok`.
+                constexpr int PRE = NOUT < 128 ? NOUT : 128;
                 const bool has_r1 = ok && (p.res1_hi != nullptr), has_r2 = ok && (p.res2_hi != nullptr);
-#pragma unroll 1
-                for (int cc = 0; cc < NOUT; cc += 16) {
-                    float v[16];
-                    uint4 r1[4], r2[4];
-                    if (has_r1) {  // issue the residual loads before the TMEM read
-                        const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o + cc);
-                        const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o + cc);
-                        r1[0] = gh[0]; r1[1] = gh[1]; r1[2] = gl[0]; r1[3] = gl[1];
-                    }
-                    if (has_r2) {
-                        const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o + cc);
-                        const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o + cc);
-                        r2[0] = gh[0]; r2[1] = gh[1]; r2[2] = gl[0]; r2[3] = gl[1];
-                    }
-                    pair_acc16<NA, STACK>(taddr, cc, v);
+                uint4 rh[PRE / 8], rl[PRE / 8];
+#pragma unroll
+                for (int h0 = 0; h0 < NOUT; h0 += PRE) {
                     if (has_r1) {
-                        add_split8(v, r1[0], r1[2]);
-                        add_split8(v + 8, r1[1], r1[3]);
+                        const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o + h0);
+                        const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o + h0);
+#pragma unroll
+                        for (int i = 0; i < PRE / 8; ++i) {
+                            rh[i] = gh[i];
+                            rl[i] = gl[i];
+                        }
                     }
-                    if (has_r2) {
-                        add_split8(v, r2[0], r2[2]);
-                        add_split8(v + 8, r2[1], r2[3]);
+                    if (h0 == 0) {
+                        mbar_wait(&tfull[ab], aphase);
+                        tc_fence_after();
                     }
-                    if (ok) store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
+#pragma unroll
+                    for (int c1 = 0; c1 < PRE; c1 += 16) {
+                        const int cc = h0 + c1;
+                        float v[16];
+                        pair_acc16<NA, STACK>(taddr, cc, v);
+                        if (has_r1) {
+                            add_split8(v, rh[c1 / 8], rl[c1 / 8]);
+                            add_split8(v + 8, rh[c1 / 8 + 1], rl[c1 / 8 + 1]);
+                        }
+                        if (has_r2) {
+                            const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o + cc);
+                            const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o + cc);
+                            add_split8(v, gh[0], gl[0]);
+                            add_split8(v + 8, gh[1], gl[1]);
+                        }
+                        if (ok) store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader);
             } else {
+                mbar_wait(&tfull[ab], aphase);
+                tc_fence_after();
                 const int t = pt * NT + nt;
                 float* prow0 = p.partial + ((size_t)t * p.nsplit * TC_BM + row) * NOUT;
                 if (live) {

@@ -434,8 +434,14 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
         p.S = S; p.H = H >> lvl; p.W = W >> lvl; p.Cin = NC[lvl]; p.Cout = NC[lvl];
         p.relu = relu;
         tiles(p);
-        if ((net->tc_pair >> lvl) & 1) {
-            tc_slab_tile_shape(p.W, p.H, &p.BW, &p.BH);
+        // CTA-pair kernel when the layer fills the machine with pair tiles; the single-CTA kernel (finer tiles, split-K)
+        // for the small layers of small slice batches, which are latency- rather than throughput-bound
+        int SW, SH;
+        tc_slab_tile_shape(p.W, p.H, &SW, &SH);
+        const int pair_groups = ((((p.W + SW - 1) / SW) * ((p.H + SH - 1) / SH) * S + 1) / 2) * (NC[lvl] >= 256 ? NC[lvl] / 256 : 1);
+        if (((net->tc_pair >> lvl) & 1) && (pair_groups >= ctx->sm_count / 2 || (net->tc_pair & 16))) {
+            p.BW = SW;
+            p.BH = SH;
             p.tiles_x = (p.W + p.BW - 1) / p.BW;
             p.tiles_y = (p.H + p.BH - 1) / p.BH;
             p.mapA_hi[0] = &net->amap_slab[src][lvl][0]; p.mapA_lo[0] = &net->amap_slab[src][lvl][1];

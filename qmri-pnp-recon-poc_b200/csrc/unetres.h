@@ -19,7 +19,7 @@ struct qmri_net {
     std::vector<float*> w[2];   // packed device weights per layer, [0] PyTorch planes, [1] MATLAB planes
     float* ws = nullptr;        // activation workspace
     size_t ws_elems = 0;
-    int max_chunk = 8;          // slices evaluated per pass through the network
+    int max_chunk = 16;         // slices evaluated per pass through the network
     int chunk = 0;
     float* io = nullptr;        // staging for the host entry points
     size_t io_elems = 0;
