@@ -66,52 +66,63 @@ def synthetic_slices(S, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons DURING the timed region through NVML.  Samples are taken by the timing loop itself right
+    after each step has been enqueued (the GPU is then busy executing it, the host has nothing to launch): a background
+    `nvidia-smi -lms` child or NVML thread was measured to stall this process's kernel launches for tens of ms per query
+    (driver lock), inflating the single-slice loop by up to 4x.  Falls back to one nvidia-smi query per sample."""
 
-    def __init__(self, gpu_index):
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, gpu_index, period_s=0.05):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.period = period_s
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.nvml = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.idx
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                phys = int(vis.split(",")[self.idx])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def sample(self):
+        try:
+            self._sample()
+        except Exception:
+            pass
+
+    def _sample(self):
+        if self.nvml is not None:
+            self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+            mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            for nm, bit in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(nm)
+            return
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        self.sm.append(float(f[0]))
+        self.mx = float(f[1])
+        for nm, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+            if val.lower().startswith("active"):
+                self.reasons.add(nm)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["clock sampling unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_loop(n_iters, threads, seed=0):
@@ -218,7 +229,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
         barrier()
@@ -228,6 +239,8 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(steps):
             flush.zero_()          # evict L2 between steps (256 MiB > 126 MB L2)
             fn()
+            if sampler is not None:
+                sampler.sample()   # the step is enqueued and executing: clocks under load, host idle
         e1.record(stream)
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)), ctx.launch_count - l0
@@ -237,7 +250,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, launches = timed(lambda: sess.run(iters), args.steps, args.warmup)
+    ms_dev, launches = timed(lambda: sess.run(iters), args.steps, args.warmup, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     value = world * S * iters * args.steps / (ms_dev * 1e-3)
 

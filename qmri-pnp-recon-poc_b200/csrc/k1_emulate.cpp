@@ -18,15 +18,17 @@ template <int MC>
 static void emulate(int mode, int C, int S, const optab::K1Tables& t, const float* in_re, const float* in_im,
                     const float* v, const float* y, float rho, float* out_re, float* out_im, float* y_out,
                     float* minmax) {
-    constexpr int THREADS = 8 * MC, CL = NF / MC, GROUPS = THREADS / 16, ROUNDS = MC / GROUPS, WPG = (MC + 31) / 32;
+    constexpr int THREADS = 8 * MC, CL = NF / MC, GROUPS = THREADS / 16, ROUNDS = MC / GROUPS;
     const float2* tw = reinterpret_cast<const float2*>(t.tw.data());
+    std::vector<float2> twp(TWP, float2{0, 0});  // padded copy, as the kernel builds it in shared memory
+    for (int i = 0; i < NF; ++i) twp[i + (i >> 4)] = tw[i];
     const size_t plane = (size_t)NF * NF;
     for (int s = 0; s < S; ++s) {
         float lmin = INFINITY, lmax = -INFINITY;
         for (int c = 0; c < C; ++c) {
             const int f0 = t.frame_ptr[c], ns = t.frame_ptr[c + 1] - f0;
             std::vector<std::vector<float2>> cols(CL, std::vector<float2>((size_t)MC * CS, float2{0, 0}));
-            std::vector<std::vector<float2>> pc(CL, std::vector<float2>(t.ns_max, float2{0, 0}));
+            std::vector<std::vector<float2>> pc(CL, std::vector<float2>(t.ns_max + 1, float2{0, 0}));  // [ns_max] stays zero
             const size_t base = ((size_t)(s * C + c)) * plane;
             auto run_fft = [&](int r, bool inv) {
                 for (int rd = 0; rd < ROUNDS; ++rd) {
@@ -69,11 +71,11 @@ static void emulate(int mode, int C, int S, const optab::K1Tables& t, const floa
                     run_fft(r, false);
                     for (int j = 0; j < ns; ++j) {
                         uint16_t kk = t.samp[f0 + j];
-                        pc[r][j] = sampled_dft_partial<MC>(cols[r].data(), tw, r * MC, kk & 0xff, kk >> 8);
+                        pc[r][j] = sampled_dft_partial<MC>(cols[r].data(), twp.data(), r * MC, kk & 0xff, kk >> 8);
                     }
                 }
                 const float inv_n = 1.0f / (float)NF;
-                std::vector<float2> cfull(t.ns_max);
+                std::vector<float2> cfull(t.ns_max + 1, float2{0, 0});
                 for (int j = 0; j < ns; ++j) {
                     float sx = 0.f, sy = 0.f;
                     for (int r = 0; r < CL; ++r) {
@@ -103,14 +105,9 @@ static void emulate(int mode, int C, int S, const optab::K1Tables& t, const floa
             }
             for (int r = 0; r < CL; ++r) {
                 for (int tid = 0; tid < THREADS; ++tid) {
-                    int warp = tid >> 5, lane = tid & 31;
-                    int g = warp / WPG, mm = (warp % WPG) * 32 + lane;
-                    if (mm < MC && g < NROWGRP) {
-                        const uint16_t* row_ptr = t.row_ptr.data() + (size_t)c * (NF + 1);
-                        int r0 = t.row_grp[c * (NROWGRP + 1) + g], r1 = t.row_grp[c * (NROWGRP + 1) + g + 1];
-                        sparse_idft_rows(cols[r].data() + mm * CS, pc[r].data(), tw, row_ptr, t.rowtab.data() + f0,
-                                         r * MC + mm, r0, r1);
-                    }
+                    const int mm = tid % MC, ph = tid / MC;
+                    sparse_idft_flat(cols[r].data() + mm * CS, pc[r].data(), twp.data(),
+                                     t.p4tab.data() + ((size_t)c * optab::K1_PHASES + ph) * t.p4_len, t.p4_len, r * MC + mm);
                 }
                 run_fft(r, true);
                 const size_t slab = base + (size_t)r * MC * NF;

@@ -74,54 +74,62 @@ struct K1Tables {
     std::vector<int> frame_ptr;       // [C+1]
     std::vector<int32_t> idx;         // [nmeas]
     std::vector<uint16_t> samp;       // [nmeas]
-    std::vector<uint16_t> row_ptr;    // [C][225]
-    std::vector<uint32_t> rowtab;     // [nmeas]
-    std::vector<int> row_grp;         // [C][8]
+    std::vector<uint32_t> p4tab;      // [C][8][p4_len] flat work lists of the sparse inverse pass (see build_k1_tables)
+    int p4_len = 0;
     std::vector<float> tw;            // [224][2]
 };
 
+constexpr int K1_PHASES = 8;          // row phases of the sparse inverse pass = THREADS / MC of the kernel
+// p4tab entry: k2 | k1 << 8 | j << 16 | last_of_row << 31; j == ns_max addresses a zero coefficient (empty rows, padding)
+static inline uint32_t p4_entry(int k2, int k1, int j, bool last) {
+    return (uint32_t)k2 | ((uint32_t)k1 << 8) | ((uint32_t)j << 16) | (last ? 0x80000000u : 0u);
+}
+
 static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t) {
-    const int NG = 7;
     t.C = (int)frames.size();
     t.frame_ptr.assign(t.C + 1, 0);
     for (int c = 0; c < t.C; ++c) t.frame_ptr[c + 1] = t.frame_ptr[c] + (int)frames[c].size();
     t.nmeas = t.frame_ptr[t.C];
     t.ns_max = 0;
+    t.p4_len = 0;
     t.idx.clear();
     t.samp.clear();
-    t.row_ptr.assign((size_t)t.C * (N + 1), 0);
-    t.rowtab.assign(t.nmeas, 0);
-    t.row_grp.assign((size_t)t.C * (NG + 1), 0);
+    std::vector<std::vector<std::vector<uint32_t>>> lists(t.C, std::vector<std::vector<uint32_t>>(K1_PHASES));
+    for (int c = 0; c < t.C; ++c) t.ns_max = std::max(t.ns_max, (int)frames[c].size());
     for (int c = 0; c < t.C; ++c) {
         const auto& f = frames[c];
         int ns = (int)f.size();
-        t.ns_max = std::max(t.ns_max, ns);
-        std::vector<int> cnt(N + 1, 0);
+        std::vector<std::vector<std::pair<int, int>>> rows(N);  // per k1: (k2, j), ascending j keeps k2 ascending
         for (int j = 0; j < ns; ++j) {
             int k1 = f[j] % N, k2 = f[j] / N;
             t.idx.push_back(f[j]);
             t.samp.push_back((uint16_t)(k1 | (k2 << 8)));
-            cnt[k1 + 1]++;
+            rows[k1].push_back({k2, j});
         }
-        uint16_t* rp = &t.row_ptr[(size_t)c * (N + 1)];
-        rp[0] = 0;
-        for (int k = 0; k < N; ++k) rp[k + 1] = (uint16_t)(rp[k] + cnt[k + 1]);
-        std::vector<int> fill(rp, rp + N);
-        for (int j = 0; j < ns; ++j) {  // ascending j keeps k2 ascending inside a row
-            int k1 = f[j] % N, k2 = f[j] / N;
-            t.rowtab[t.frame_ptr[c] + fill[k1]++] = (uint32_t)k2 | ((uint32_t)j << 8);
+        // Sparse inverse pass: every row k1 of the slab must be written (rows without samples with zero).  Rows are dealt
+        // to K1_PHASES work lists of equal cost (largest first onto the lightest list); a thread owns one column and one
+        // list and walks it with a single uniform loop: accumulate c_j e^{+2 pi i k2 m / N}, store at the row's last entry.
+        std::vector<int> order(N);
+        for (int k = 0; k < N; ++k) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
+        std::vector<size_t> cost(K1_PHASES, 0);
+        for (int k1 : order) {
+            int ph = (int)(std::min_element(cost.begin(), cost.end()) - cost.begin());
+            auto& L = lists[c][ph];
+            if (rows[k1].empty()) {
+                L.push_back(p4_entry(0, k1, t.ns_max, true));
+            } else {
+                for (size_t e = 0; e < rows[k1].size(); ++e)
+                    L.push_back(p4_entry(rows[k1][e].first, k1, rows[k1][e].second, e + 1 == rows[k1].size()));
+            }
+            cost[ph] = L.size();
         }
-        // contiguous row ranges with balanced cost (1 per row + 1 per sample)
-        double total = N + ns, acc = 0;
-        int* rg = &t.row_grp[(size_t)c * (NG + 1)];
-        int g = 1;
-        rg[0] = 0;
-        for (int k = 0; k < N && g < NG; ++k) {
-            acc += 1 + cnt[k + 1];
-            if (acc >= total * g / NG) rg[g++] = k + 1;
-        }
-        while (g <= NG) rg[g++] = N;
+        for (int ph = 0; ph < K1_PHASES; ++ph) t.p4_len = std::max(t.p4_len, (int)lists[c][ph].size());
     }
+    t.p4tab.assign((size_t)t.C * K1_PHASES * t.p4_len, p4_entry(0, 0, t.ns_max, false));  // padding: adds zero, stores nothing
+    for (int c = 0; c < t.C; ++c)
+        for (int ph = 0; ph < K1_PHASES; ++ph)
+            std::copy(lists[c][ph].begin(), lists[c][ph].end(), t.p4tab.begin() + ((size_t)c * K1_PHASES + ph) * t.p4_len);
     t.tw.resize(2 * N);
     const double PI = 3.14159265358979323846;
     for (int i = 0; i < N; ++i) {

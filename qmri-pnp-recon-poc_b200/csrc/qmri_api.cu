@@ -234,9 +234,7 @@ struct qmri_op {
     float2* d_tw = nullptr;
     int* d_frame_ptr = nullptr;
     uint16_t* d_samp = nullptr;
-    uint16_t* d_row_ptr = nullptr;
-    uint32_t* d_rowtab = nullptr;
-    int* d_row_grp = nullptr;
+    uint32_t* d_p4tab = nullptr;
     // scratch for the host entry points
     DevBuf stage, a_re, a_im, b_re, b_im, c_re, c_im, ybuf, mm_ord, mm_f;
     size_t plane() const { return (size_t)N * M * C; }
@@ -275,9 +273,7 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     r |= dev_alloc(&op->d_tw, (size_t)N);
     r |= dev_alloc(&op->d_frame_ptr, (size_t)C + 1);
     r |= dev_alloc(&op->d_samp, nm);
-    r |= dev_alloc(&op->d_row_ptr, t.row_ptr.size());
-    r |= dev_alloc(&op->d_rowtab, nm);
-    r |= dev_alloc(&op->d_row_grp, t.row_grp.size());
+    r |= dev_alloc(&op->d_p4tab, std::max<size_t>(t.p4tab.size(), 1));
     if (r) {
         qmri_op_destroy(op);
         return QMRI_ENOMEM;
@@ -285,9 +281,7 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     cudaMemcpy(op->d_tw, t.tw.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_frame_ptr, t.frame_ptr.data(), sizeof(int) * (C + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_samp, t.samp.data(), sizeof(uint16_t) * t.nmeas, cudaMemcpyHostToDevice);
-    cudaMemcpy(op->d_row_ptr, t.row_ptr.data(), sizeof(uint16_t) * t.row_ptr.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(op->d_rowtab, t.rowtab.data(), sizeof(uint32_t) * t.nmeas, cudaMemcpyHostToDevice);
-    cudaError_t e = cudaMemcpy(op->d_row_grp, t.row_grp.data(), sizeof(int) * t.row_grp.size(), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(op->d_p4tab, t.p4tab.data(), sizeof(uint32_t) * t.p4tab.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         qmri_op_destroy(op);
         return qmri_fail(QMRI_ECUDA, "operator table upload failed: %s", cudaGetErrorString(e));
@@ -324,7 +318,7 @@ extern "C" int qmri_op_destroy(qmri_op* op) {
     DevSetter ds(op->ctx->device);
     cudaStreamSynchronize(op->ctx->stream);
     cudaFree(op->d_tw); cudaFree(op->d_frame_ptr); cudaFree(op->d_samp);
-    cudaFree(op->d_row_ptr); cudaFree(op->d_rowtab); cudaFree(op->d_row_grp);
+    cudaFree(op->d_p4tab);
     op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
     op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
     delete op;
@@ -343,9 +337,8 @@ static void k1_fill_tables(const qmri_op* op, K1Params& p) {
     p.tw = op->d_tw;
     p.frame_ptr = op->d_frame_ptr;
     p.samp = op->d_samp;
-    p.row_ptr = op->d_row_ptr;
-    p.rowtab = op->d_rowtab;
-    p.row_grp = op->d_row_grp;
+    p.p4tab = op->d_p4tab;
+    p.p4_len = op->t.p4_len;
     p.C = op->C;
     p.nmeas = op->t.nmeas;
 }
@@ -568,6 +561,13 @@ struct qmri_admm {
     DevBuf y, x0_re, x0_im, w_re, w_im, v, x_re, x_im, mm_ord, mm_f, noise, cb_in, cb_out;
     float *h_in = nullptr, *h_out = nullptr;  // pinned, host-callback path
     bool uploaded = false;
+    // one steady-state ADMM iteration (x-update, min/max, 64-conv denoiser = ~130 launches) captured as a CUDA graph:
+    // at small slice batches the loop is otherwise bound by the host's launch rate
+    cudaGraphExec_t graph = nullptr;
+    const void* graph_ws = nullptr;  // denoiser workspace / chunk / precision the graph was captured with
+    int graph_chunk = 0, graph_prec = -1;
+    int64_t graph_launches = 0;
+    bool graph_failed = false;
 };
 
 extern "C" int qmri_admm_create(qmri_op* op, int S, const qmri_admm_params* params, qmri_admm** out) {
@@ -637,6 +637,7 @@ extern "C" int qmri_admm_destroy(qmri_admm* st) {
     st->noise.release(); st->cb_in.release(); st->cb_out.release();
     if (st->h_in) cudaFreeHost(st->h_in);
     if (st->h_out) cudaFreeHost(st->h_out);
+    if (st->graph) cudaGraphExecDestroy(st->graph);
     delete st;
     return QMRI_OK;
 }
@@ -729,7 +730,7 @@ extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
     QCUDA(cudaMemcpyAsync(st->x_re.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     QCUDA(cudaMemcpyAsync(st->x_im.p, st->x0_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     QCHECK(k1_minmax_init(ctx, st->mm_ord.as<int>(), S));
-    for (int k = 0; k < iters; ++k) {
+    auto iteration = [&](int k) -> int {
         if (k == 0) {
             dim3 grid(std::min<unsigned>(nblk(op->plane()), 256), S);
             add_minmax_kernel<<<grid, 256, 0, ctx->stream>>>(st->w_re.as<float>(), st->w_im.as<float>(), nullptr, nullptr, nullptr,
@@ -740,7 +741,49 @@ extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
         }
         minmax_finalize_kernel<<<nblk(S, 128), 128, 0, ctx->stream>>>(st->mm_ord.as<int>(), st->mm_f.as<float>(), S);
         QLAUNCH_CHECK(ctx);
-        QCHECK(admm_denoise(st));
+        return admm_denoise(st);
+    };
+    // Iterations 2 .. iters-2 launch the same kernels with the same arguments: capture one and replay it.  Iterations 0 and 1
+    // run directly first, so every lazy initialisation (workspaces, tensor maps, function attributes) is done before capture.
+    qmri_net* net = st->prm.net;
+    const bool want_graph = net && !st->graph_failed && iters >= 6 && !getenv("QMRI_NO_GRAPH") && !getenv("QMRI_PROFILE") && !getenv("QMRI_TC_TRACE");
+    for (int k = 0; k < iters; ++k) {
+        if (!(want_graph && k >= 2 && k < iters - 1)) {
+            QCHECK(iteration(k));
+            continue;
+        }
+        if (st->graph && (st->graph_ws != net->ws || st->graph_chunk != net->chunk || st->graph_prec != net->precision)) {
+            cudaGraphExecDestroy(st->graph);  // the denoiser workspace moved or its mode changed since the capture
+            st->graph = nullptr;
+        }
+        if (!st->graph) {
+            const int64_t l0 = ctx->launches;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+            int rc = QMRI_OK;
+            if (e == cudaSuccess) {
+                rc = iteration(k);
+                e = cudaStreamEndCapture(ctx->stream, &g);
+            }
+            if (e == cudaSuccess && rc == QMRI_OK && g) e = cudaGraphInstantiate(&st->graph, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (e != cudaSuccess || rc != QMRI_OK || !st->graph) {
+                cudaGetLastError();
+                st->graph = nullptr;
+                st->graph_failed = true;  // fall back to direct launches for the rest of this state's life
+                ctx->launches = l0;
+                QCHECK(iteration(k));
+                for (++k; k < iters; ++k) QCHECK(iteration(k));
+                return QMRI_OK;
+            }
+            st->graph_launches = ctx->launches - l0;
+            ctx->launches = l0;
+            st->graph_ws = net->ws;
+            st->graph_chunk = net->chunk;
+            st->graph_prec = net->precision;
+        }
+        QCUDA(cudaGraphLaunch(st->graph, ctx->stream));
+        ctx->launches += st->graph_launches;  // kernels inside the replayed graph
     }
     return QMRI_OK;
 }

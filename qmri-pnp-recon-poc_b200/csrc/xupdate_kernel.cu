@@ -23,7 +23,6 @@ struct K1Cfg {
     static constexpr int CL = NF / MC;              // cluster size
     static constexpr int GROUPS = THREADS / 16;     // concurrent column FFTs
     static constexpr int ROUNDS = MC / GROUPS;      // == 2
-    static constexpr int WPG = (MC + 31) / 32;      // warps per row group in the sparse inverse pass
     static constexpr int F4_PER_THREAD = (MC * NF / 4) / THREADS;  // == 7
 };
 
@@ -38,8 +37,11 @@ __global__ void __launch_bounds__(K1Cfg<MC>::THREADS) xupdate_kernel(K1Params p)
     constexpr int CL = Cfg::CL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* cols = reinterpret_cast<float2*>(smem_raw);            // [MC][CS]
-    float2* tw = cols + MC * CS;                                   // [224]
-    float2* pc = tw + NF;                                          // [ns_max] partial sums, then c
+    float2* tw = cols + MC * CS;                                   // [224] twiddles (FFT stages)
+    float2* twp = tw + NF;                                         // [238] padded copy (sparse passes)
+    float2* pc = twp + TWP;                                        // [ns_max + 1] partial sums, then c; pc[ns_max] == 0
+    uint32_t* s_p4 = reinterpret_cast<uint32_t*>(pc + p.ns_max + 1);  // [8][p4_len] work lists of the sparse inverse pass
+    uint16_t* s_samp = reinterpret_cast<uint16_t*>(s_p4 + K1_PHASES * p.p4_len);  // [ns_max] k1 | k2 << 8
     __shared__ float red_min[32], red_max[32];
 
     cg::cluster_group cluster = cg::this_cluster();
@@ -54,7 +56,15 @@ __global__ void __launch_bounds__(K1Cfg<MC>::THREADS) xupdate_kernel(K1Params p)
     const size_t plane = (size_t)NF * NF;
     const size_t slab = ((size_t)(s * p.C + c)) * plane + (size_t)m0 * NF;  // contiguous MC*224 floats
 
-    for (int i = tid; i < NF; i += THREADS) tw[i] = p.tw[i];
+    // per-frame operator tables -> shared memory (the sparse passes walk them once per column / sample)
+    for (int i = tid; i < NF; i += THREADS) {
+        const float2 t = p.tw[i];
+        tw[i] = t;
+        twp[i + (i >> 4)] = t;
+    }
+    for (int i = tid; i < ns; i += THREADS) s_samp[i] = p.samp[f0 + i];
+    for (int i = tid; i < K1_PHASES * p.p4_len; i += THREADS) s_p4[i] = p.p4tab[(size_t)c * K1_PHASES * p.p4_len + i];
+    if (tid == 0) pc[p.ns_max] = make_float2(0.f, 0.f);
 
     // ---- P1: load z into shared memory ---------------------------------------------
     if (mode != K1_ADJOINT) {
@@ -98,8 +108,8 @@ __global__ void __launch_bounds__(K1Cfg<MC>::THREADS) xupdate_kernel(K1Params p)
 
         // ---- P3: sampled DFT along m (partial over this slab) ---------------------------
         for (int j = tid; j < ns; j += THREADS) {
-            uint16_t kk = p.samp[f0 + j];
-            pc[j] = sampled_dft_partial<MC>(cols, tw, m0, kk & 0xff, kk >> 8);
+            uint16_t kk = s_samp[j];
+            pc[j] = sampled_dft_partial<MC>(cols, twp, m0, kk & 0xff, kk >> 8);
         }
         cluster.sync();
 
@@ -149,14 +159,8 @@ __global__ void __launch_bounds__(K1Cfg<MC>::THREADS) xupdate_kernel(K1Params p)
 
     // ---- P4: sparse inverse DFT along m: every (column, row) of the slab is rewritten ------
     {
-        const int warp = tid >> 5, lane = tid & 31;
-        const int g = warp / Cfg::WPG;
-        const int mm = (warp % Cfg::WPG) * 32 + lane;
-        if (mm < MC && g < NROWGRP) {
-            const uint16_t* row_ptr = p.row_ptr + c * (NF + 1);
-            const int r0 = p.row_grp[c * (NROWGRP + 1) + g], r1 = p.row_grp[c * (NROWGRP + 1) + g + 1];
-            sparse_idft_rows(cols + mm * CS, pc, tw, row_ptr, p.rowtab + f0, m0 + mm, r0, r1);
-        }
+        const int mm = tid % MC, ph = tid / MC;  // THREADS = 8 MC: column mm, work list ph
+        sparse_idft_flat(cols + mm * CS, pc, twp, s_p4 + ph * p.p4_len, p.p4_len, m0 + mm);
     }
     __syncthreads();
 
@@ -240,11 +244,12 @@ __global__ void __launch_bounds__(K1Cfg<MC>::THREADS) xupdate_kernel(K1Params p)
 template <int MC>
 static int launch_mc(qmri_ctx* ctx, const K1Params& p, int S, int ns_max) {
     using Cfg = K1Cfg<MC>;
-    size_t smem = (size_t)(MC * CS + NF + ns_max) * sizeof(float2);
-    static bool configured = false;
-    if (!configured) {
-        QCUDA(cudaFuncSetAttribute(xupdate_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
-        configured = true;
+    static_assert(Cfg::THREADS / MC == K1_PHASES, "one work list per row phase");
+    size_t smem = (size_t)(MC * CS + NF + TWP + ns_max + 1) * sizeof(float2) + (size_t)K1_PHASES * p.p4_len * 4 + (size_t)ns_max * 2 + 16;
+    static size_t configured = 0;  // the table sizes depend on the operator: raise the limit when a larger one comes along
+    if (smem > configured) {
+        QCUDA(cudaFuncSetAttribute(xupdate_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(Cfg::CL, p.C, S);
@@ -263,8 +268,10 @@ static int launch_mc(qmri_ctx* ctx, const K1Params& p, int S, int ns_max) {
     return QMRI_OK;
 }
 
-int k1_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max, int mc) {
+int k1_launch(qmri_ctx* ctx, const K1Params& p_in, int S, int ns_max, int mc) {
     if (S <= 0) return QMRI_OK;
+    K1Params p = p_in;
+    p.ns_max = ns_max;
     if (mc == 56) return launch_mc<56>(ctx, p, S, ns_max);
     return launch_mc<28>(ctx, p, S, ns_max);
 }

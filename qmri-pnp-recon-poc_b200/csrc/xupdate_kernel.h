@@ -5,6 +5,8 @@
 
 struct qmri_ctx;
 
+constexpr int K1_PHASES = 8;  // == optab::K1_PHASES
+
 enum { K1_ADMM = 0, K1_SOLVE = 1, K1_FORWARD = 2, K1_ADJOINT = 3 };
 
 struct K1Params {
@@ -23,11 +25,11 @@ struct K1Params {
     const float2* tw;        // [224] e^{-2 pi i t / 224}
     const int* frame_ptr;    // [C+1]
     const uint16_t* samp;    // [nmeas] k1 | k2 << 8, frame-major, ascending k = k1 + 224 k2
-    const uint16_t* row_ptr; // [C][225] CSR over k1 rows of each frame
-    const uint32_t* rowtab;  // [nmeas] per frame, row-sorted: k2 | (j << 8)
-    const int* row_grp;      // [C][8] row ranges balancing the sparse inverse pass over 7 warp groups
+    const uint32_t* p4tab;   // [C][8][p4_len] flat work lists of the sparse inverse pass (op_tables.h)
+    int p4_len;
     int C;
     int nmeas;
+    int ns_max;              // largest per-frame sample count (sizes the shared-memory tables; set by k1_launch)
     int mode;
     float inv_1p_rho;
 };

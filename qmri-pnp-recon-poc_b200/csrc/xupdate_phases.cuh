@@ -30,7 +30,7 @@ namespace k1 {
 
 constexpr int NF = 224;   // image side (N == M == 224) and FFT length
 constexpr int CS = 225;   // shared-memory column stride in float2 (odd: conflict-free across columns)
-constexpr int NROWGRP = 7;
+constexpr int TWP = NF + NF / 16;  // padded twiddle table: entry t sits at t + (t >> 4), so strided lookups spread over banks
 
 QHD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 QHD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -169,12 +169,12 @@ QHD void fft_s2_store(float2* col, int k1, const float2 (&b)[16]) {
 // ---- sparse m-direction transforms -------------------------------------------------
 // forward: partial sum over this CTA's columns of  T[m][k1] * e^{-2 pi i k2 m / 224}
 template <int MC>
-QHD float2 sampled_dft_partial(const float2* cols, const float2* tw, int m0, int k1, int k2) {
+QHD float2 sampled_dft_partial(const float2* cols, const float2* twp, int m0, int k1, int k2) {
     int idx = (k2 * m0) % NF;
     float ax = 0.f, ay = 0.f;
 #pragma unroll 4
     for (int mm = 0; mm < MC; ++mm) {
-        float2 t = tw[idx];
+        float2 t = twp[idx + (idx >> 4)];
         float2 v = cols[mm * CS + k1];
         ax = fmaf(v.x, t.x, ax);
         ax = fmaf(-v.y, t.y, ax);
@@ -186,24 +186,27 @@ QHD float2 sampled_dft_partial(const float2* cols, const float2* tw, int m0, int
     return make_float2(ax, ay);
 }
 
-// inverse: column m of the sparse k-space array, rows [r0, r1): T'[m][k1] = sum_j c_j e^{+2 pi i k2_j m / 224}
-// row_ptr: CSR over k1 for this frame (225 entries), rowtab[e] = k2 | (j << 8)
-QHD void sparse_idft_rows(float2* col, const float2* c, const float2* tw, const uint16_t* row_ptr,
-                          const uint32_t* rowtab, int m, int r0, int r1) {
-    for (int k1 = r0; k1 < r1; ++k1) {
-        int e0 = row_ptr[k1], e1 = row_ptr[k1 + 1];
-        float ax = 0.f, ay = 0.f;
-        for (int e = e0; e < e1; ++e) {
-            uint32_t ent = rowtab[e];
-            int k2 = ent & 0xff;
-            float2 cj = c[ent >> 8];
-            float2 t = tw[(k2 * m) % NF];  // conj(t) = e^{+...}
-            ax = fmaf(cj.x, t.x, ax);
-            ax = fmaf(cj.y, t.y, ax);
-            ay = fmaf(cj.y, t.x, ay);
-            ay = fmaf(-cj.x, t.y, ay);
+// inverse: column m of the sparse k-space array,  T'[m][k1] = sum_{j in row k1} c_j e^{+2 pi i k2_j m / 224}.
+// `tab` is one of the 8 flat work lists of the frame (op_tables.h): entries k2 | k1 << 8 | j << 16 | last << 31, padded to a
+// common length, so the thread (one column m, one list) runs a single branch-free loop and stores a row at its last entry;
+// rows without samples appear as one entry with the zero coefficient c[ns_max].  twp: padded twiddles.
+QHD void sparse_idft_flat(float2* col, const float2* c, const float2* twp, const uint32_t* tab, int len, int m) {
+    float ax = 0.f, ay = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < len; ++i) {
+        const uint32_t en = tab[i];
+        const float2 cj = c[(en >> 16) & 0x7fff];
+        const uint32_t idx = ((en & 0xff) * (uint32_t)m) % NF;
+        const float2 t = twp[idx + (idx >> 4)];  // conj(t) = e^{+...}
+        ax = fmaf(cj.x, t.x, ax);
+        ax = fmaf(cj.y, t.y, ax);
+        ay = fmaf(cj.y, t.x, ay);
+        ay = fmaf(-cj.x, t.y, ay);
+        if (en & 0x80000000u) {
+            col[(en >> 8) & 0xff] = make_float2(ax, ay);
+            ax = 0.f;
+            ay = 0.f;
         }
-        col[k1] = make_float2(ax, ay);
     }
 }
 
