@@ -229,10 +229,12 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, collective=True):
+        """collective=False: a leg only rank 0 runs (no barrier / all-reduce, which the other ranks would never join)."""
+        sync = barrier if collective else torch.cuda.synchronize
         for _ in range(warmup):
             fn()
-        barrier()
+        sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launch_count
         e0.record(stream)
@@ -242,8 +244,9 @@ def run_ours(args, rank, world, local_rank):
             if sampler is not None:
                 sampler.sample()   # the step is enqueued and executing: clocks under load, host idle
         e1.record(stream)
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1)), ctx.launch_count - l0
+        sync()
+        ms = e0.elapsed_time(e1)
+        return (max_over_ranks(ms) if collective else ms), ctx.launch_count - l0
 
     # ---- value: loop only, inputs resident in HBM -----------------------------------------------------
     sess.upload_raw(Yp, X0p)
@@ -278,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_forward": ms_fwd / 5, "precision_mode": args.precision}
     # K1 at a batch larger than L2 (algorithmic bytes: 20 B per pixel-channel per iteration)
     roof_k1 = None
-    if rank == 0 and not args.skip_extra:
+    if rank == 0 and world == 1 and not args.skip_extra:  # single-GPU run only: the scaling runs stay short
         S1 = args.k1_slices
         Xb = synthetic_slices(S1, seed=5)
         Yb = F.forward(Xb)
@@ -286,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
         sess1.upload(Yb, F.adjoint(Yb))
         sess1.run(1)
         reps = 20
-        ms_k1, _ = timed(lambda: sess1.xupdate_only(reps), 3, 2)
+        ms_k1, _ = timed(lambda: sess1.xupdate_only(reps), 3, 2, collective=False)
         t_launch = ms_k1 * 1e-3 / (3 * reps)
         gbs = 20.0 * hw * C_CH * S1 / t_launch / 1e9
         roof_k1 = {"bound": "hbm", "kernel": "xupdate_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -307,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
         def match():
             q._capi.check(ctx.lib.qmri_match_dev(d.handle, C.c_void_p(xr.data_ptr()), C.c_void_p(xi.data_ptr()), npix,
                                                  C.c_void_p(qm.data_ptr()), C.c_void_p(pdv.data_ptr()), None, None))
-        ms_m, _ = timed(match, 3, 2)
+        ms_m, _ = timed(match, 3, 2, collective=False)
         pxa = npix * K * 3 / (ms_m * 1e-3)
         fp32_peak = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
         roof_k2 = {"bound": "fp32", "kernel": "match_kernel", "achieved": pxa * 40 / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -344,6 +347,7 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line))
     sess.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -381,6 +385,12 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extra", action="store_true")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched by hand without torchrun: start one rank per GPU the way the driver does
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -273,6 +273,42 @@ def test_denoiser_multi_level_11_channels(q):
     assert rel_l2(net.forward(x.numpy()), ref) <= TOL_DENOISER
 
 
+def test_match_atom_sharded_equals_unsharded(q):
+    """BASELINE config 5 on one GPU: two atom shards scored separately, keys max-combined, finish -> identical to the
+    unsharded match (the same packed keys are what ranks all-reduce with MAX; tests/test_sharding_gloo.py covers the exchange)."""
+    import torch
+    from oracle import synth
+    d = synth.make_dictionary(K_target=6000, cut=3, seed=1)
+    K = np.asarray(d["D"]).shape[0]
+    rng = np.random.default_rng(4)
+    npix = 5000
+    xr = torch.from_numpy(rng.standard_normal((10, npix)).astype(np.float32)).cuda()
+    xi = torch.from_numpy(rng.standard_normal((10, npix)).astype(np.float32)).cuda()
+    full = q.Dictionary(d)
+    qm0, pd0, mt0, dm0 = q.mrf_dtm_sharded(full, xr, xi, npix, want_mt=True)
+    keys = []
+    import ctypes as C
+    for r in range(2):
+        sh = q.Dictionary(d, shard=q.atom_shard(K, 2, r))
+        k = torch.zeros(npix, dtype=torch.int64, device="cuda")
+        q._capi.check(sh.ctx.lib.qmri_match_keys_dev(sh.handle, C.c_void_p(xr.data_ptr()), C.c_void_p(xi.data_ptr()), npix, C.c_void_p(k.data_ptr())))
+        sh.ctx.synchronize()
+        keys.append(k)
+        sh.close()
+    merged = torch.maximum(keys[0], keys[1])
+    dm = torch.empty(npix, dtype=torch.int32, device="cuda")
+    qm = torch.empty(2 * npix, dtype=torch.float32, device="cuda")
+    pd = torch.empty(2 * npix, dtype=torch.float32, device="cuda")
+    q._capi.check(full.ctx.lib.qmri_match_finish_dev(full.handle, C.c_void_p(xr.data_ptr()), C.c_void_p(xi.data_ptr()), npix,
+                                                    C.c_void_p(merged.data_ptr()), C.c_void_p(qm.data_ptr()), C.c_void_p(pd.data_ptr()), None,
+                                                    C.c_void_p(dm.data_ptr())))
+    full.ctx.synchronize()
+    assert torch.equal(dm, dm0) and torch.equal(qm.view(2, npix), qm0) and torch.equal(pd.view(npix, 2), pd0)
+    score, idx = q.unpack_keys(merged.cpu().numpy().view(np.uint64))
+    assert np.array_equal(idx + 1, dm0.cpu().numpy())
+    full.close()
+
+
 # ---------------------------------------------------------------------------------------------
 def box_denoiser(v):
     """A cheap deterministic stand-in for param.net: 5-point average on the first 10 channels."""
