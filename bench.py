@@ -66,8 +66,8 @@ def synthetic_slices(S, seed):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region through NVML.  Samples are taken by the timing loop itself right
-    after each step has been enqueued (the GPU is then busy executing it, the host has nothing to launch): a background
+    """SM clock / throttle reasons DURING the timed region through NVML.  Samples are taken by the timing loop itself once
+    all timed steps have been enqueued (the GPU is then busy executing them, the host has nothing to launch): a background
     `nvidia-smi -lms` child or NVML thread was measured to stall this process's kernel launches for tens of ms per query
     (driver lock), inflating the single-slice loop by up to 4x.  Falls back to one nvidia-smi query per sample."""
 
@@ -93,6 +93,8 @@ class ClockSampler:
             self.nvml = pynvml
         except Exception:
             self.nvml = None
+        self.sample()              # first query outside the timed region (lazy NVML initialisation takes ~0.5 s)
+        self.sm, self.reasons = [], set()
 
     def sample(self):
         try:
@@ -241,9 +243,12 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(steps):
             flush.zero_()          # evict L2 between steps (256 MiB > 126 MB L2)
             fn()
-            if sampler is not None:
-                sampler.sample()   # the step is enqueued and executing: clocks under load, host idle
         e1.record(stream)
+        if sampler is not None:    # every step is enqueued: sample clocks while the GPU works through them (host idle)
+            sampler.sample()
+            while not e1.query():
+                time.sleep(0.1)    # sparse on purpose: every NVML query measurably perturbs the running kernels
+                sampler.sample()
         sync()
         ms = e0.elapsed_time(e1)
         return (max_over_ranks(ms) if collective else ms), ctx.launch_count - l0
