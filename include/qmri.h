@@ -192,9 +192,11 @@ int qmri_match_keys_dev(qmri_dict* d, const float* x_re, const float* x_im, int6
 int qmri_match_finish_dev(qmri_dict* d, const float* x_re, const float* x_im, int64_t npix, const uint64_t* keys_dev,
                           float* qmap_dev, float* pd_dev, float* mt_dev, int32_t* dm_dev);
 
-/* ---- TSMI synthesis (next row) -------------------------------------
- * main_synthesize_tsmis.m:84-98: nearest (T1,T2) atom, scale by normD*|PD|, sign-align to
- * channel 1.  qmap: npix x 3 column-major (T1,T2,PD) host float32 -> X npix x C float32. */
+/* ---- TSMI synthesis ------------------------------------------------
+ * main_synthesize_tsmis.m:84-98: I = knnsearch(KDTreeSearcher(dict.lut), qm(:,1:2)) as an exhaustive fused
+ * nearest-(T1,T2) scan on the GPU, X = D(I,:) .* normD(I) .* |PD|, sign-aligned to channel 1.
+ * qmap: npix x 3 column-major (T1,T2,PD) host float32 -> X npix x C column-major float32;
+ * atom_index (optional): 1-based I.  Exact distance ties resolve to the lowest atom index. */
 int qmri_synthesize(qmri_dict* d, const float* qmap, int64_t npix, float* X, int32_t* atom_index);
 
 #ifdef __cplusplus

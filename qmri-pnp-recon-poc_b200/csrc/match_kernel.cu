@@ -202,6 +202,103 @@ int launch_c(qmri_ctx* ctx, const K2Params& p) {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// K4 - TSMI synthesis, the mirror image of K2 (argmin of a distance instead of argmax of a correlation).
+//
+// Reference being replaced: main_synthesize_tsmis.m:84-98
+//   I = knnsearch(KDTreeSearcher(dict.lut), qm(:,1:2));  X = real(dict.D(I,1:10)) .* dict.normD(I) .* abs(qm(:,3));
+//   X = X .* sign(X(:,:,1))
+// The KD-tree is replaced by an exhaustive fused scan: every thread keeps PX pixels' (T1, T2) in registers, the
+// (T1, T2) pairs of the atoms stream through shared memory, per (pixel, atom) 2 FADD + FMUL + FFMA + one FMNMX
+// (running minimum of a 16-atom group; the group is rescanned for the first atom attaining it).  The packed key
+// float_bits(d^2) << 32 | atom merges atom ranges with atomicMin (smallest distance, lowest index on exact ties).
+// ------------------------------------------------------------------------------------------------
+constexpr int K4_CHUNK = 2048;
+
+template <int PX>
+__global__ void __launch_bounds__(K2_THREADS) synth_nn_kernel(K4Params p) {
+    __shared__ float s1[K4_CHUNK], s2[K4_CHUNK];
+    const int tid = threadIdx.x;
+    const int64_t pix0 = (int64_t)blockIdx.x * (K2_THREADS * PX);
+    const int64_t per = (p.K + gridDim.y - 1) / gridDim.y;
+    const int64_t ka = (int64_t)blockIdx.y * per, kb = min(p.K, ka + per);
+    float a1[PX], a2[PX], best[PX];
+    int bgrp[PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        const int64_t pix = pix0 + tid + (int64_t)i * K2_THREADS;
+        const bool ok = pix < p.npix;
+        a1[i] = ok ? __ldg(p.t1 + pix) : 0.f;
+        a2[i] = ok ? __ldg(p.t2 + pix) : 0.f;
+        best[i] = INFINITY;
+        bgrp[i] = 0;
+    }
+    for (int64_t k0 = ka; k0 < kb; k0 += K4_CHUNK) {
+        const int nk = (int)min((int64_t)K4_CHUNK, kb - k0);
+        const int ngrp = (nk + K2_GROUP - 1) / K2_GROUP;
+        __syncthreads();
+        for (int i = tid; i < ngrp * K2_GROUP; i += K2_THREADS) {  // atoms past the range sit at infinity: never nearest
+            s1[i] = (i < nk) ? __ldg(p.lut + k0 + i) : INFINITY;
+            s2[i] = (i < nk) ? __ldg(p.lut + p.K + k0 + i) : INFINITY;
+        }
+        __syncthreads();
+        const int g0 = (int)((k0 - ka) / K2_GROUP);
+#pragma unroll 1
+        for (int g = 0; g < ngrp; ++g) {
+            float gmin[PX];
+#pragma unroll
+            for (int i = 0; i < PX; ++i) gmin[i] = INFINITY;
+#pragma unroll
+            for (int a = 0; a < K2_GROUP; ++a) {
+                const float l1 = s1[g * K2_GROUP + a], l2 = s2[g * K2_GROUP + a];
+#pragma unroll
+                for (int i = 0; i < PX; ++i) {
+                    const float d1 = a1[i] - l1, d2 = a2[i] - l2;
+                    gmin[i] = fminf(gmin[i], fmaf(d2, d2, d1 * d1));  // fminf drops NaN (NaN LUT rows never match)
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PX; ++i)
+                if (gmin[i] < best[i]) {  // strict: the first group wins exact ties
+                    best[i] = gmin[i];
+                    bgrp[i] = g0 + g;
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        const int64_t pix = pix0 + tid + (int64_t)i * K2_THREADS;
+        if (pix >= p.npix || !(best[i] < INFINITY)) continue;
+        const int64_t kg = ka + (int64_t)bgrp[i] * K2_GROUP;
+        int64_t win = kg;
+        for (int a = 0; a < K2_GROUP; ++a) {
+            const int64_t k = kg + a;
+            if (k >= kb) break;
+            const float d1 = a1[i] - __ldg(p.lut + k), d2 = a2[i] - __ldg(p.lut + p.K + k);
+            if (fmaf(d2, d2, d1 * d1) == best[i]) {
+                win = k;
+                break;
+            }
+        }
+        const unsigned long long key = ((unsigned long long)__float_as_uint(best[i]) << 32) | (unsigned long long)(unsigned)win;
+        atomicMin(p.keys + pix, key);
+    }
+}
+
+// X = D(I,:) .* normD(I) .* |PD|, then X .* sign(X(:,1))   (main_synthesize_tsmis.m:89-98)
+__global__ void synth_render_kernel(K4Params p) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.npix) return;
+    const unsigned long long key = p.keys[pix];
+    int64_t idx = (int64_t)(key & 0xFFFFFFFFull);
+    if (key == ~0ull || idx >= p.K) idx = 0;  // NaN query: knnsearch still returns an index; take the first atom
+    const float sc = __ldg(p.normD + idx) * fabsf(__ldg(p.pd + pix));
+    const float x0 = __ldg(p.Dp + idx * p.CP) * sc;
+    const float sg = (x0 > 0.f) ? 1.f : (x0 < 0.f ? -1.f : 0.f);  // MATLAB sign(): sign(0) = 0
+    for (int c = 0; c < p.C; ++c) p.X[(int64_t)c * p.npix + pix] = __ldg(p.Dp + idx * p.CP + c) * sc * sg;
+    if (p.index) p.index[pix] = (int32_t)idx + 1;
+}
+
 int k2_padded_channels(int C) { return (C + 3) / 4 * 4; }
 
 int k2_launch_keys(qmri_ctx* ctx, const K2Params& p) {
@@ -218,6 +315,20 @@ int k2_launch_keys(qmri_ctx* ctx, const K2Params& p) {
 int k2_launch_finish(qmri_ctx* ctx, const K2Finish& p) {
     if (p.npix <= 0) return QMRI_OK;
     match_finish_kernel<<<(unsigned)((p.npix + 255) / 256), 256, 0, ctx->stream>>>(p);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+
+int k4_launch(qmri_ctx* ctx, const K4Params& p) {
+    if (p.npix <= 0) return QMRI_OK;
+    constexpr int PX = 4;
+    const int64_t ppb = (int64_t)K2_THREADS * PX;
+    const int64_t gx = (p.npix + ppb - 1) / ppb;
+    int64_t gy = std::max<int64_t>(1, std::min<int64_t>((2LL * ctx->sm_count + gx - 1) / gx, std::max<int64_t>(1, p.K / K4_CHUNK)));
+    QCUDA(cudaMemsetAsync(p.keys, 0xFF, (size_t)p.npix * 8, ctx->stream));
+    synth_nn_kernel<PX><<<dim3((unsigned)gx, (unsigned)gy), K2_THREADS, 0, ctx->stream>>>(p);
+    QLAUNCH_CHECK(ctx);
+    synth_render_kernel<<<(unsigned)((p.npix + 255) / 256), 256, 0, ctx->stream>>>(p);
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
 }

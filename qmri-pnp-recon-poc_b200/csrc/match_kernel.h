@@ -33,3 +33,20 @@ struct K2Finish {
 int k2_padded_channels(int C);
 int k2_launch_keys(qmri_ctx* ctx, const K2Params& p);
 int k2_launch_finish(qmri_ctx* ctx, const K2Finish& p);
+
+// K4 - TSMI synthesis (main_synthesize_tsmis.m:84-98): nearest (T1, T2) atom + render
+struct K4Params {
+    const float* t1;     // [npix]
+    const float* t2;     // [npix]
+    const float* pd;     // [npix]
+    int64_t npix;
+    const float* lut;    // [Q][K] column-major K x Q, Q >= 2: lut[0][k] = T1, lut[1][k] = T2
+    const float* Dp;     // [K][CP]
+    const float* normD;  // [K]
+    int64_t K;
+    int C, CP;
+    unsigned long long* keys;  // [npix] scratch
+    float* X;            // [C][npix] planar output
+    int32_t* index;      // optional [npix], 1-based nearest atom
+};
+int k4_launch(qmri_ctx* ctx, const K4Params& p);

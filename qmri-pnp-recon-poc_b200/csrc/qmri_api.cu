@@ -934,6 +934,32 @@ extern "C" int qmri_match(qmri_dict* d, const void* x, int x_dtype, int64_t npix
 }
 
 extern "C" int qmri_synthesize(qmri_dict* d, const float* qmap, int64_t npix, float* X, int32_t* atom_index) {
-    (void)d; (void)qmap; (void)npix; (void)X; (void)atom_index;
-    return qmri_fail(QMRI_EUNSUPPORTED, "qmri_synthesize (SURVEY.md 8f-1, main_synthesize_tsmis.m:84-98) is not built yet");
+    if (!d || (npix > 0 && (!qmap || !X))) return qmri_fail(QMRI_EINVAL, "qmri_synthesize: null argument");
+    if (npix < 0) return qmri_fail(QMRI_EINVAL, "npix < 0");
+    if (d->Q < 2) return qmri_fail(QMRI_EINVAL, "qmri_synthesize needs dict.lut with (T1, T2) columns, got Q = %d", d->Q);
+    if (npix == 0) return QMRI_OK;
+    qmri_ctx* ctx = d->ctx;
+    DevSetter ds(ctx->device);
+    const size_t n = (size_t)npix;
+    // stage: [T1 | T2 | PD] planes (the host array is npix x 3 column-major = exactly this), then X [C][npix]
+    QCHECK(d->stage.ensure(n * 3 * 4));
+    QCHECK(d->x_re.ensure(n * d->C * 4));
+    QCHECK(d->keys.ensure(n * 8));
+    QCHECK(d->dm.ensure(n * 4));
+    QCUDA(cudaMemcpyAsync(d->stage.p, qmap, n * 3 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    K4Params p = {};
+    p.t1 = d->stage.as<float>();
+    p.t2 = p.t1 + n;
+    p.pd = p.t1 + 2 * n;
+    p.npix = npix;
+    p.lut = d->lut; p.Dp = d->Dp; p.normD = d->normD;
+    p.K = d->K; p.C = d->C; p.CP = d->CP;
+    p.keys = d->keys.as<unsigned long long>();
+    p.X = d->x_re.as<float>();
+    p.index = atom_index ? d->dm.as<int32_t>() : nullptr;
+    QCHECK(k4_launch(ctx, p));
+    QCUDA(cudaMemcpyAsync(X, p.X, n * d->C * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (atom_index) QCUDA(cudaMemcpyAsync(atom_index, p.index, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    QCUDA(cudaStreamSynchronize(ctx->stream));
+    return QMRI_OK;
 }

@@ -113,3 +113,25 @@ def mrf_dtm_cpu(dict_, data, par=None):
 
 
 mrf_dtm = mrf_dtm_cpu
+
+
+def synthesize_tsmis(dict_, qmap_slice, return_index=False):
+    """``main_synthesize_tsmis.m:84-98`` for one slice: ``qmap_slice`` ``[3 x N x M]`` (T1, T2, PD) -> X ``[N x M x C]`` real
+    single (what the script saves); ``return_index`` also returns the 0-based nearest atom per pixel (pixel n + N m)."""
+    own = not isinstance(dict_, Dictionary)
+    d = Dictionary(dict_) if own else dict_
+    try:
+        q3 = np.asarray(qmap_slice)
+        if q3.ndim != 3 or q3.shape[0] != 3:
+            raise ValueError("qmap slice must be [3 x N x M] (T1, T2, PD)")
+        _, N, M = q3.shape
+        qm = np.asfortranarray(np.transpose(q3, (1, 2, 0)).reshape((-1, 3), order="F").astype(np.float32))  # :84-87
+        npix = qm.shape[0]
+        X = np.zeros((npix, d.C), np.float32, order="F")
+        I = np.zeros(npix, np.int32)
+        check(d.ctx.lib.qmri_synthesize(d.handle, ptr(qm), npix, ptr(X), ptr(I)))
+        X = X.reshape((N, M, d.C), order="F")
+        return (X, I.astype(np.int64) - 1) if return_index else X
+    finally:
+        if own:
+            d.close()

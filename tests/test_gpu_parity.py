@@ -273,6 +273,31 @@ def test_denoiser_multi_level_11_channels(q):
     assert rel_l2(net.forward(x.numpy()), ref) <= TOL_DENOISER
 
 
+def test_synthesize_tsmis_matches_oracle(q):
+    """main_synthesize_tsmis.m:84-98 on the GPU (exhaustive nearest-(T1,T2) scan) vs the cKDTree restatement.
+    Indices must agree except where the float64 oracle's two nearest atoms are (nearly) equidistant; X follows from the index."""
+    from scipy.spatial import cKDTree
+    from oracle import synth
+    d = synth.make_dictionary(K_target=9000, cut=3, seed=2)
+    qmap = synth.make_qmaps(seed=3, S=2, N=230, M=230)[1]          # [3 x 230 x 230], zero background
+    Xo, Io = synth.synthesize_tsmis(d, qmap)
+    X, I = q.synthesize_tsmis(d, qmap, return_index=True)
+    assert X.shape == (230, 230, 10) and X.dtype == np.float32
+    qm = np.transpose(qmap, (1, 2, 0)).reshape((-1, 3), order="F")
+    dist, _ = cKDTree(np.asarray(d["lut"], np.float64)).query(qm[:, :2].astype(np.float64), k=2)
+    decided = (dist[:, 1] - dist[:, 0]) > 1e-5 * np.maximum(dist[:, 1], 1e-12)      # the GPU scan works on the float32 qmap
+    assert decided.mean() > 0.3                                     # the phantom has large decided regions besides the background
+    assert np.array_equal(I[decided], Io[decided])
+    same = (I == Io).reshape((230, 230), order="F")
+    assert rel_l2(X[same], Xo[same]) <= 1e-6
+    assert np.all(X[:, :, 0] >= 0)                                  # channel 1 sign-aligned (:97-98)
+    # the synthesized slice drives the rest of the path: crop 4:227 like main_recon_tsmis_FFT.m:212 and match it back
+    out = q.mrf_dtm_cpu(d, {"X": X[3:227, 3:227, :]}, {"f": {"qout": 1, "pdout": 1, "dmout": 1}})
+    fg = (np.abs(qmap[2, 3:227, 3:227]) > 0) & same[3:227, 3:227]
+    lut = np.asarray(d["lut"])
+    assert np.allclose(out["qmap"][fg][:, 0], lut[I.reshape((230, 230), order="F")[3:227, 3:227][fg], 0], rtol=0.03)
+
+
 def test_match_atom_sharded_equals_unsharded(q):
     """BASELINE config 5 on one GPU: two atom shards scored separately, keys max-combined, finish -> identical to the
     unsharded match (the same packed keys are what ranks all-reduce with MAX; tests/test_sharding_gloo.py covers the exchange)."""
