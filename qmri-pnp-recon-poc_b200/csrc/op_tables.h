@@ -77,6 +77,12 @@ struct K1Tables {
     std::vector<uint32_t> p4tab;      // [C][8][p4_len] flat work lists of the sparse inverse pass (see build_k1_tables)
     int p4_len = 0;
     std::vector<float> tw;            // [224][2]
+    // streaming kernel (xupdate_stream.cu): the sparse m-direction sums are evaluated per k-space row k1, one thread per row
+    std::vector<uint8_t> rowmap;      // [C][N]   row k1 owned by thread tid
+    std::vector<uint16_t> row_ptr;    // [C][N+1] offsets (relative to the frame) of thread tid's samples in `items`
+    std::vector<uint32_t> items;      // [nmeas]  j | k2 << 16, frame-major, grouped by owning thread
+    int max_row = 0;                  // largest number of samples in one row of one frame
+    std::vector<float> tw2;           // [16][16][2]  e^{-2 pi i (i j) / N}
 };
 
 constexpr int K1_PHASES = 8;          // row phases of the sparse inverse pass = THREADS / MC of the kernel
@@ -130,8 +136,42 @@ static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>
     for (int c = 0; c < t.C; ++c)
         for (int ph = 0; ph < K1_PHASES; ++ph)
             std::copy(lists[c][ph].begin(), lists[c][ph].end(), t.p4tab.begin() + ((size_t)c * K1_PHASES + ph) * t.p4_len);
+    // Row tables of the streaming kernel.  Thread tid = 16 h + l owns the row of residue class l (k1 = l mod 16) that has
+    // the h-th most samples in its class: the 16 lanes of a half-warp then address 16 different bank pairs (conflict-free
+    // 64-bit shared-memory accesses to [mm][k1]) and the rows of a warp carry similar sample counts (little divergence).
+    t.rowmap.assign((size_t)t.C * N, 0);
+    t.row_ptr.assign((size_t)t.C * (N + 1), 0);
+    t.items.assign(std::max(t.nmeas, 1), 0);
+    t.max_row = 0;
+    if (N % 16 == 0) {
+        for (int c = 0; c < t.C; ++c) {
+            const auto& f = frames[c];
+            std::vector<std::vector<uint32_t>> rows(N);
+            for (int j = 0; j < (int)f.size(); ++j) rows[f[j] % N].push_back((uint32_t)j | ((uint32_t)(f[j] / N) << 16));
+            for (int k = 0; k < N; ++k) t.max_row = std::max(t.max_row, (int)rows[k].size());
+            const int H = N / 16;
+            for (int l = 0; l < 16; ++l) {
+                std::vector<int> cls(H);
+                for (int q = 0; q < H; ++q) cls[q] = l + 16 * q;
+                std::stable_sort(cls.begin(), cls.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
+                for (int h = 0; h < H; ++h) t.rowmap[(size_t)c * N + 16 * h + l] = (uint8_t)cls[h];
+            }
+            size_t pos = 0;
+            for (int tid = 0; tid < N; ++tid) {
+                t.row_ptr[(size_t)c * (N + 1) + tid] = (uint16_t)pos;
+                for (uint32_t e : rows[t.rowmap[(size_t)c * N + tid]]) t.items[t.frame_ptr[c] + pos++] = e;
+            }
+            t.row_ptr[(size_t)c * (N + 1) + N] = (uint16_t)pos;
+        }
+    }
     t.tw.resize(2 * N);
     const double PI = 3.14159265358979323846;
+    t.tw2.resize(2 * 256);
+    for (int i = 0; i < 16; ++i)
+        for (int j = 0; j < 16; ++j) {
+            t.tw2[2 * (16 * i + j)] = (float)cos(-2.0 * PI * (i * j) / N);
+            t.tw2[2 * (16 * i + j) + 1] = (float)sin(-2.0 * PI * (i * j) / N);
+        }
     for (int i = 0; i < N; ++i) {
         t.tw[2 * i] = (float)cos(-2.0 * PI * i / N);
         t.tw[2 * i + 1] = (float)sin(-2.0 * PI * i / N);

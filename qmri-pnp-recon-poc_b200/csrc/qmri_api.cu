@@ -235,6 +235,11 @@ struct qmri_op {
     int* d_frame_ptr = nullptr;
     uint16_t* d_samp = nullptr;
     uint32_t* d_p4tab = nullptr;
+    float2* d_tw2 = nullptr;
+    uint8_t* d_rowmap = nullptr;
+    uint16_t* d_row_ptr = nullptr;
+    uint32_t* d_items = nullptr;
+    int k1_kernel = 0;  // 0 = choose by batch size, 1 = cluster kernel, 2 = streaming kernel (QMRI_K1_KERNEL=cluster|stream)
     // scratch for the host entry points
     DevBuf stage, a_re, a_im, b_re, b_im, c_re, c_im, ybuf, mm_ord, mm_f;
     size_t plane() const { return (size_t)N * M * C; }
@@ -266,6 +271,9 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     op->N = N; op->M = M; op->C = C; op->L = L;
     const char* env = getenv("QMRI_K1_MC");
     if (env && atoi(env) == 56) op->k1_mc = 56;
+    env = getenv("QMRI_K1_KERNEL");
+    if (env && !strcmp(env, "cluster")) op->k1_kernel = 1;
+    if (env && !strcmp(env, "stream")) op->k1_kernel = 2;
     optab::build_k1_tables(N, frames, op->t);
     const optab::K1Tables& t = op->t;
     size_t nm = std::max(1, t.nmeas);
@@ -274,6 +282,10 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     r |= dev_alloc(&op->d_frame_ptr, (size_t)C + 1);
     r |= dev_alloc(&op->d_samp, nm);
     r |= dev_alloc(&op->d_p4tab, std::max<size_t>(t.p4tab.size(), 1));
+    r |= dev_alloc(&op->d_tw2, (size_t)256);
+    r |= dev_alloc(&op->d_rowmap, t.rowmap.size());
+    r |= dev_alloc(&op->d_row_ptr, t.row_ptr.size());
+    r |= dev_alloc(&op->d_items, t.items.size());
     if (r) {
         qmri_op_destroy(op);
         return QMRI_ENOMEM;
@@ -281,6 +293,10 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     cudaMemcpy(op->d_tw, t.tw.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_frame_ptr, t.frame_ptr.data(), sizeof(int) * (C + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_samp, t.samp.data(), sizeof(uint16_t) * t.nmeas, cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_tw2, t.tw2.data(), sizeof(float) * t.tw2.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_rowmap, t.rowmap.data(), t.rowmap.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_row_ptr, t.row_ptr.data(), sizeof(uint16_t) * t.row_ptr.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_items, t.items.data(), sizeof(uint32_t) * t.items.size(), cudaMemcpyHostToDevice);
     cudaError_t e = cudaMemcpy(op->d_p4tab, t.p4tab.data(), sizeof(uint32_t) * t.p4tab.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         qmri_op_destroy(op);
@@ -319,6 +335,7 @@ extern "C" int qmri_op_destroy(qmri_op* op) {
     cudaStreamSynchronize(op->ctx->stream);
     cudaFree(op->d_tw); cudaFree(op->d_frame_ptr); cudaFree(op->d_samp);
     cudaFree(op->d_p4tab);
+    cudaFree(op->d_tw2); cudaFree(op->d_rowmap); cudaFree(op->d_row_ptr); cudaFree(op->d_items);
     op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
     op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
     delete op;
@@ -333,12 +350,33 @@ extern "C" int qmri_op_indices(const qmri_op* op, int32_t* idx, int64_t* frame_p
     return QMRI_OK;
 }
 
+// Kernel choice for one x-update launch: the streaming kernel (one CTA per slice-channel, xupdate_stream.cu) once the batch
+// fills the machine, the cluster kernel (eight CTAs per slice-channel, xupdate_kernel.cu) for small batches and for masks
+// with densely sampled k-space rows (EPI lines).  QMRI_K1_KERNEL=cluster|stream forces one (tests, profiling).
+static int k1_dispatch(const qmri_op* op, const K1Params& p, int S) {
+    qmri_ctx* ctx = op->ctx;
+    const bool can_stream = k1_stream_supported(op->t.max_row, op->t.ns_max);
+    bool stream = can_stream && (long long)S * op->C >= K1_STREAM_MIN_CTAS_PER_SM * (long long)ctx->sm_count;
+    if (op->k1_kernel == 1) stream = false;
+    if (op->k1_kernel == 2) {
+        if (!can_stream)
+            return qmri_fail(QMRI_EUNSUPPORTED, "QMRI_K1_KERNEL=stream: a k-space row of this mask holds %d samples (limit %d)", op->t.max_row, 24);
+        stream = true;
+    }
+    if (stream) return k1_stream_launch(ctx, p, S, op->t.ns_max);
+    return k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc);
+}
+
 static void k1_fill_tables(const qmri_op* op, K1Params& p) {
     p.tw = op->d_tw;
     p.frame_ptr = op->d_frame_ptr;
     p.samp = op->d_samp;
     p.p4tab = op->d_p4tab;
     p.p4_len = op->t.p4_len;
+    p.tw2 = op->d_tw2;
+    p.rowmap = op->d_rowmap;
+    p.row_ptr = op->d_row_ptr;
+    p.items = op->d_items;
     p.C = op->C;
     p.nmeas = op->t.nmeas;
 }
@@ -392,7 +430,7 @@ extern "C" int qmri_forward(qmri_op* op, const void* x, int x_dtype, int S, void
     p.in_re = op->a_re.as<float>();
     p.in_im = dtype_is_complex(x_dtype) ? op->a_im.as<float>() : nullptr;
     p.y_out = op->ybuf.as<float2>();
-    QCHECK(k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc));
+    QCHECK(k1_dispatch(op, p, S));
     if (n) {
         QCHECK(op->stage.ensure(n * dtype_size(y_dtype)));
         if (y_dtype == QMRI_C64) cvt_c_out_kernel<float><<<nblk(n), 256, 0, ctx->stream>>>((float*)op->stage.p, op->ybuf.as<float2>(), n);
@@ -420,7 +458,7 @@ extern "C" int qmri_adjoint(qmri_op* op, const void* y, int y_dtype, int S, void
     p.y = op->ybuf.as<float2>();
     p.out_re = op->a_re.as<float>();
     p.out_im = op->a_im.as<float>();
-    QCHECK(k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc));
+    QCHECK(k1_dispatch(op, p, S));
     return image_download(op, x, x_dtype, S, op->a_re.as<float>(), op->a_im.as<float>());
 }
 
@@ -451,7 +489,7 @@ extern "C" int qmri_xupdate(qmri_op* op, double rho, const void* y, int y_dtype,
     p.y = op->ybuf.as<float2>();
     p.out_re = ar; p.out_im = ai;                                                // a = x
     p.inv_1p_rho = (float)(1.0 / (1.0 + rho));
-    QCHECK(k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc));
+    QCHECK(k1_dispatch(op, p, S));
     QCHECK(image_download(op, x, x_dtype, S, ar, ai));
     if (w || minmax) {
         QCHECK(op->mm_ord.ensure(2 * S * sizeof(int)));
@@ -677,7 +715,7 @@ static int admm_k1(qmri_admm* st, bool write_x) {
     p.y = st->y.as<float2>();
     p.minmax = st->mm_ord.as<int>();
     p.inv_1p_rho = (float)(1.0 / (1.0 + st->prm.gamma));
-    return k1_launch(op->ctx, p, st->S, op->t.ns_max, op->k1_mc);
+    return k1_dispatch(op, p, st->S);
 }
 
 static int admm_denoise(qmri_admm* st) {

@@ -27,6 +27,11 @@ struct K1Params {
     const uint16_t* samp;    // [nmeas] k1 | k2 << 8, frame-major, ascending k = k1 + 224 k2
     const uint32_t* p4tab;   // [C][8][p4_len] flat work lists of the sparse inverse pass (op_tables.h)
     int p4_len;
+    // streaming kernel tables (xupdate_stream.cu; op_tables.h)
+    const float2* tw2;       // [16][16] e^{-2 pi i (i j) / 224}
+    const uint8_t* rowmap;   // [C][224] k-space row owned by thread tid
+    const uint16_t* row_ptr; // [C][225] offsets of thread tid's samples in `items`, relative to the frame
+    const uint32_t* items;   // [nmeas] j | k2 << 16, frame-major, grouped by owning thread
     int C;
     int nmeas;
     int ns_max;              // largest per-frame sample count (sizes the shared-memory tables; set by k1_launch)
@@ -35,4 +40,8 @@ struct K1Params {
 };
 
 int k1_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max, int mc);
+constexpr int K1_STREAM_MIN_CTAS_PER_SM = 2;  // use the streaming kernel from S * C >= 2 * SM count on
+// streaming variant: one CTA per (slice, channel); needs <= RMAX_STREAM samples per k-space row
+bool k1_stream_supported(int max_row, int ns_max);
+int k1_stream_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max);
 int k1_minmax_init(qmri_ctx* ctx, int* minmax, int S);

@@ -210,4 +210,100 @@ QHD void sparse_idft_flat(float2* col, const float2* c, const float2* twp, const
     }
 }
 
+
+// =====================================================================================
+// Streaming variant (xupdate_stream.cu): one CTA walks the eight 28-column slabs of a
+// (slice, channel) image one after the other, so no cluster exchange is needed.
+//  * the first forward stage takes its 14 inputs from registers (loaded straight from
+//    global memory), the last inverse stage leaves its 14 outputs in registers (stored
+//    straight to global memory): two shared-memory passes fewer per transform;
+//  * the inverse transform runs radix 16 first, radix 14 last, so that a half-warp's
+//    outputs n = c + 16 d are 16 consecutive floats in global memory;
+//  * the sparse m-direction sums are evaluated per k-space ROW k1: the thread keeps the
+//    28 slab values of its row in registers and walks the row's samples with a rotating
+//    twiddle (t <- t * e^{-+2 pi i k2 / 224}), so the inner loops touch no shared memory.
+// tw2[i][j] = e^{-2 pi i (i j) / 224}, i, j < 16: stage twiddles, lanes contiguous in j.
+// =====================================================================================
+constexpr int RMAX_STREAM = 24;  // rows with more samples than this need the cluster kernel (e.g. EPI lines)
+
+// forward stage 1 on register inputs: a[n1] = x[16 n1 + n2]
+QHD void fwd_s1_regs(float2 (&a)[16], int n2, const float2* tw2) {
+    dft14(a);
+#pragma unroll
+    for (int k1 = 1; k1 < 14; ++k1) a[k1] = cmul(a[k1], tw2[16 * k1 + n2]);
+}
+
+// inverse transform of one column via the swap identity  ifft(U) = swap(fft(swap(U))) (unnormalised):
+// input index k = 14 a + b, output index n = c + 16 d
+//   X[c + 16 d] = sum_b w14^{b d} [ w224^{b c} sum_a U[14 a + b] w16^{a c} ]
+QHD void inv_s1_load(const float2* col, int b, const float2* tw2, float2 (&x)[16]) {
+#pragma unroll
+    for (int a = 0; a < 16; ++a) x[a] = cswap(col[14 * a + b]);
+    dft16(x);
+#pragma unroll
+    for (int c = 1; c < 16; ++c) x[c] = cmul(x[c], tw2[16 * c + b]);
+}
+QHD void inv_s1_store(float2* col, int b, const float2 (&x)[16]) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) col[swz(b, c)] = x[c];
+}
+// leaves x[d] = (inverse transform)[c + 16 d], d = 0..13
+QHD void inv_s2_regs(const float2* col, int c, float2 (&x)[16]) {
+#pragma unroll
+    for (int b = 0; b < 14; ++b) x[b] = col[swz(b, c)];
+    dft14(x);
+#pragma unroll
+    for (int d = 0; d < 14; ++d) x[d] = cswap(x[d]);
+}
+
+// sampled forward DFT along m for the samples of one row k1: items[q] = j | k2 << 16.
+// pc[j] += sum_mm T[mm][k1] e^{-2 pi i k2 (m0 + mm) / 224}
+template <int MC>
+QHD void p3_row(const float2* ws, int k1, const uint32_t* items, int cnt, const float2* tw, int m0, float2* pc) {
+    if (cnt == 0) return;
+    float2 T[MC];
+#pragma unroll
+    for (int mm = 0; mm < MC; ++mm) T[mm] = ws[mm * CS + k1];
+    for (int q = 0; q < cnt; ++q) {
+        const uint32_t en = items[q];
+        const int k2 = (int)(en >> 16), j = (int)(en & 0xffffu);
+        float2 t = tw[(k2 * m0) % NF];
+        const float2 st = tw[k2];
+        float ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int mm = 0; mm < MC; ++mm) {
+            ax = fmaf(T[mm].x, t.x, ax);
+            ax = fmaf(-T[mm].y, t.y, ax);
+            ay = fmaf(T[mm].x, t.y, ay);
+            ay = fmaf(T[mm].y, t.x, ay);
+            t = cmul(t, st);
+        }
+        float2 o = pc[j];
+        pc[j] = make_float2(o.x + ax, o.y + ay);
+    }
+}
+
+// sparse inverse DFT along m for one row k1:  U[mm][k1] = sum_j c_j e^{+2 pi i k2_j (m0 + mm) / 224}
+template <int MC>
+QHD void p4_row(float2* ws, int k1, const uint32_t* items, int cnt, const float2* tw, int m0, const float2* pc) {
+    float2 U[MC];
+#pragma unroll
+    for (int mm = 0; mm < MC; ++mm) U[mm] = make_float2(0.f, 0.f);
+    for (int q = 0; q < cnt; ++q) {
+        const uint32_t en = items[q];
+        const int k2 = (int)(en >> 16), j = (int)(en & 0xffffu);
+        const float2 s0 = tw[(k2 * m0) % NF], s1 = tw[k2];
+        const float2 st = make_float2(s1.x, -s1.y);
+        float2 t = cmul(pc[j], make_float2(s0.x, -s0.y));
+#pragma unroll
+        for (int mm = 0; mm < MC; ++mm) {
+            U[mm].x += t.x;
+            U[mm].y += t.y;
+            t = cmul(t, st);
+        }
+    }
+#pragma unroll
+    for (int mm = 0; mm < MC; ++mm) ws[mm * CS + k1] = U[mm];
+}
+
 }  // namespace k1

@@ -421,6 +421,97 @@ def test_admm_graph_replay_equals_direct_launches(q, ops, monkeypatch):
     assert n_graph == n_direct  # kernels inside the replayed graph are counted
 
 
+
+# ---------------------------------------------------------------------------------------------
+# K1 streaming kernel (one CTA per slice-channel; chosen automatically for large slice batches)
+@pytest.fixture()
+def stream_op(q, monkeypatch):
+    from oracle import sampling
+    monkeypatch.setenv("QMRI_K1_KERNEL", "stream")
+    V = np.eye(10)
+    return q.setup_subsampling_spiralgrided(224, 224, 771, V), sampling.setup_subsampling_spiralgrided(224, 224, 771, V)
+
+
+def test_stream_kernel_operator_and_xupdate(q, stream_op):
+    from oracle.sampling import FOperator
+    from oracle.xupdate import xupdate_exact
+    P, Po = stream_op
+    F, Fo = q.fft_operator(P), FOperator(Po)
+    x = smooth_tsmi(31, S=3, cplx=True)
+    y = F.forward(x)
+    for s in range(3):
+        assert rel_l2(y[:, s], Fo.forward(x[..., s])) <= TOL_XUPDATE
+    xr = smooth_tsmi(32)                       # real input (in_im == null path)
+    assert rel_l2(F.forward(xr), Fo.forward(xr)) <= TOL_XUPDATE
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal((P.nmeas, 3)) + 1j * rng.standard_normal((P.nmeas, 3))
+    xa = F.adjoint(b)
+    for s in range(3):
+        assert rel_l2(xa[..., s], Fo.adjoint(b[:, s])) <= TOL_XUPDATE
+    assert rel_l2(F.forward(xa), b) <= TOL_XUPDATE      # A A^H = I
+    yv = Fo.forward(smooth_tsmi(33))
+    v, u = smooth_tsmi(34), 0.1 * smooth_tsmi(35, cplx=True)
+    xs, w, mm = F.xupdate(yv, v, u, 0.05, want_w=True)
+    xo = xupdate_exact(Fo, yv, v - u, 0.05)
+    assert rel_l2(xs, xo) <= TOL_XUPDATE
+    wo = xo + u
+    assert rel_l2(w, wo) <= TOL_XUPDATE
+    assert abs(mm[0] - wo.real.min()) <= 1e-5 * abs(wo.real).max()
+    assert abs(mm[1] - wo.real.max()) <= 1e-5 * abs(wo.real).max()
+
+
+def test_stream_kernel_admm_loop_and_agreement_with_cluster_kernel(q, ops, stream_op):
+    from oracle.admm import pnp_admm
+    P, Po = stream_op
+    Fo, Xgt, Y, X0 = make_problem(Po, 36, S=2)
+    Y[:, 1] *= 2.0
+    X0 = Fo.adjoint(Y)
+    param = {"iter": 5, "gamma": 0.05, "denoiser_type": "single_level"}
+    x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=box_denoiser, X0=X0))
+    for s in range(2):
+        xo = pnp_admm(Y[:, s], dict(param, F=Fo, net=box_denoiser, X0=X0[..., s]), solver="exact")
+        assert rel_l2(x[..., s], xo) <= TOL_XUPDATE
+    xc = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(ops["spiral"][0]), net=box_denoiser, X0=X0))  # cluster kernel (S*C small)
+    assert rel_l2(x, xc) <= 2e-6
+
+
+def test_stream_kernel_with_builtin_unetres_and_graph(q, stream_op):
+    from oracle import unetres
+    from oracle.admm import pnp_admm
+    P, Po = stream_op
+    Fo, Xgt, Y, X0 = make_problem(Po, 37)
+    sd = unetres.make_state_dict(10, seed=0)
+    net = q.UNetRes(sd, in_nc=10)
+    param = {"iter": 4, "gamma": 0.05, "X0": X0, "denoiser_type": "single_level"}
+    xo = pnp_admm(Y, dict(param, F=Fo, net=lambda v: unetres.denoise_matlab_layout(sd, v)), solver="exact")
+    x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=net))
+    assert rel_l2(x, xo) <= 1e-4
+
+
+def test_stream_kernel_refuses_line_sampled_masks(q, monkeypatch):
+    monkeypatch.setenv("QMRI_K1_KERNEL", "stream")
+    P = q.setup_subsampling_epi(224, 224, 1 / 65, np.eye(10))
+    with pytest.raises(q.QmriError):
+        q.fft_operator(P).forward(np.zeros((224, 224, 10)))
+
+
+def test_large_batch_takes_streaming_kernel_and_matches_oracle(q, ops):
+    """S * C >= 2 * SM count switches to the streaming kernel on its own: 32 slices, spot-check four of them."""
+    from oracle.sampling import FOperator
+    from oracle.xupdate import xupdate_exact
+    P, Po = ops["spiral"]
+    F, Fo = q.fft_operator(P), FOperator(Po)
+    S = 32
+    rng = np.random.default_rng(5)
+    base = smooth_tsmi(38, cplx=True)
+    scale = 1.0 + rng.random(S)
+    x = base[..., None] * scale
+    y = F.forward(x)
+    assert y.shape == (P.nmeas, S)
+    yo = Fo.forward(base)
+    for s in (0, 7, 19, 31):
+        assert rel_l2(y[:, s], yo * scale[s]) <= TOL_XUPDATE
+
 # ---------------------------------------------------------------------------------------------
 def test_error_behaviour(q):
     V = np.eye(10)
