@@ -139,13 +139,14 @@ static void emulate(int mode, int C, int S, const optab::K1Tables& t, const floa
     }
 }
 
-// Streaming kernel (xupdate_stream.cu): one CTA per (slice, channel), 448 threads, eight slabs walked twice.
+// Streaming kernels (xupdate_stream.cu): forward kernel per slab group (G CTAs per image, 224 threads each), solve kernel,
+// adjoint kernel - same control flow, thread by thread.
 static void emulate_stream(int mode, int C, int S, const optab::K1Tables& t, const float* in_re, const float* in_im,
                            const float* v, const float* y, float rho, float* out_re, float* out_im, float* y_out,
                            float* minmax) {
-    constexpr int MC = 28, THREADS = 16 * MC, SLABS = NF / MC, HC = MC / 2;
-    const float2* tw = reinterpret_cast<const float2*>(t.tw.data());
+    constexpr int MC = HC_STREAM, THREADS = 16 * MC, SLABS = NF / MC, G = 4, SPC = SLABS / G;
     const float2* tw2 = reinterpret_cast<const float2*>(t.tw2.data());
+    const float2* tw448 = reinterpret_cast<const float2*>(t.tw448.data());
     const size_t plane = (size_t)NF * NF;
     const float inv_n = 1.0f / (float)NF;
     for (int s = 0; s < S; ++s) {
@@ -153,91 +154,113 @@ static void emulate_stream(int mode, int C, int S, const optab::K1Tables& t, con
         for (int c = 0; c < C; ++c) {
             const int f0 = t.frame_ptr[c], ns = t.frame_ptr[c + 1] - f0;
             const size_t img = ((size_t)(s * C + c)) * plane;
-            std::vector<float2> ws((size_t)MC * CS, float2{0, 0});
-            std::vector<float2> pc((size_t)2 * t.ns_max + 1, float2{0, 0});
-            const uint32_t* items = t.items.data() + f0;
-            const uint16_t* rptr = t.row_ptr.data() + (size_t)c * (NF + 1);
-            const uint8_t* rowmap = t.rowmap.data() + (size_t)c * NF;
+            const uint32_t* ent = t.ent.data() + f0;
+            const uint32_t* itA = t.itA.data() + (size_t)c * NF;
+            const uint32_t* itB = t.itB.data() + (size_t)c * NF;
             std::vector<float2> regs((size_t)THREADS * 16);
             auto A = [&](int tid) -> float2(&)[16] { return *reinterpret_cast<float2(*)[16]>(&regs[(size_t)tid * 16]); };
+            std::vector<float2> cvec((size_t)t.ns_max + 1, float2{0, 0});
             if (mode == 3) {
                 for (int j = 0; j < ns; ++j) {
                     size_t yi = (size_t)s * t.nmeas + f0 + j;
-                    pc[j] = float2{y[2 * yi] * inv_n, y[2 * yi + 1] * inv_n};
+                    cvec[j] = float2{y[2 * yi] * inv_n, y[2 * yi + 1] * inv_n};
                 }
             } else {
-                for (int slab = 0; slab < SLABS; ++slab) {
-                    const int m0 = slab * MC;
-                    for (int tid = 0; tid < THREADS; ++tid) {
-                        const int l16 = tid & 15, col = tid >> 4;
-                        const size_t g = img + (size_t)(m0 + col) * NF + l16;
-                        float2(&a)[16] = A(tid);
-                        for (int n1 = 0; n1 < 14; ++n1) {
-                            float re = in_re[g + 16 * n1], im = in_im ? in_im[g + 16 * n1] : 0.f;
-                            if (mode == 0) {
-                                re = 2.f * v[g + 16 * n1] - re;
-                                im = -im;
+                std::vector<std::vector<float2>> part(G, std::vector<float2>((size_t)t.ns_max + 1, float2{0, 0}));
+                for (int g = 0; g < G; ++g) {  // one forward CTA
+                    std::vector<float2> ws((size_t)MC * CS, float2{0, 0});
+                    std::vector<float2>& pc = part[g];
+                    for (int sl = 0; sl < SPC; ++sl) {
+                        const int m0 = (g * SPC + sl) * MC;
+                        for (int tid = 0; tid < THREADS; ++tid) {
+                            const int l16 = tid & 15, col = tid >> 4;
+                            const size_t gi = img + (size_t)(m0 + col) * NF + l16;
+                            float2(&a)[16] = A(tid);
+                            for (int n1 = 0; n1 < 14; ++n1) {
+                                float re = in_re[gi + 16 * n1], im = in_im ? in_im[gi + 16 * n1] : 0.f;
+                                if (mode == 0) {
+                                    re = 2.f * v[gi + 16 * n1] - re;
+                                    im = -im;
+                                }
+                                a[n1] = float2{re, im};
                             }
-                            a[n1] = float2{re, im};
+                            fwd_s1_regs(a, l16, tw2);
                         }
-                        fwd_s1_regs(a, l16, tw2);
-                    }
-                    for (int tid = 0; tid < THREADS; ++tid) fft_s1_store(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
-                    for (int tid = 0; tid < THREADS; ++tid)
-                        if ((tid & 15) < 14) fft_s2_load(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
-                    for (int tid = 0; tid < THREADS; ++tid)
-                        if ((tid & 15) < 14) fft_s2_store<false>(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
-                    for (int tid = 0; tid < THREADS; ++tid) {
-                        const int half = tid >= NF ? 1 : 0, rtid = tid - half * NF;
-                        p3_row<HC>(ws.data() + half * HC * CS, rowmap[rtid], items + rptr[rtid], rptr[rtid + 1] - rptr[rtid], tw,
-                                   m0 + half * HC, pc.data() + half * t.ns_max);
+                        for (int tid = 0; tid < THREADS; ++tid) fft_s1_store(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
+                        for (int tid = 0; tid < THREADS; ++tid)
+                            if ((tid & 15) < 14) fft_s2_load(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
+                        for (int tid = 0; tid < THREADS; ++tid)
+                            if ((tid & 15) < 14) fft_s2_store<false>(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
+                        for (int tid = 0; tid < THREADS; ++tid)
+                            p3_item(ws.data(), (int)(itA[tid] & 0xffu), ent + (itA[tid] >> 16), (int)((itA[tid] >> 8) & 0xffu), tw448, m0, pc.data());
                     }
                 }
-                for (int j = 0; j < ns; ++j) {
+                for (int j = 0; j < ns; ++j) {  // solve kernel
                     size_t yi = (size_t)s * t.nmeas + f0 + j;
-                    float2 az{(pc[j].x + pc[t.ns_max + j].x) * inv_n, (pc[j].y + pc[t.ns_max + j].y) * inv_n};
+                    float sx = 0.f, sy = 0.f;
+                    for (int g = 0; g < G; ++g) {
+                        sx += part[g][j].x;
+                        sy += part[g][j].y;
+                    }
+                    sx *= inv_n;
+                    sy *= inv_n;
                     if (mode == 2) {
-                        y_out[2 * yi] = az.x;
-                        y_out[2 * yi + 1] = az.y;
+                        y_out[2 * yi] = sx;
+                        y_out[2 * yi + 1] = sy;
                     } else {
                         float gsc = (1.0f / (1.0f + rho)) * inv_n;
-                        pc[j] = float2{(y[2 * yi] - az.x) * gsc, (y[2 * yi + 1] - az.y) * gsc};
+                        cvec[j] = float2{(y[2 * yi] - sx) * gsc, (y[2 * yi + 1] - sy) * gsc};
                     }
                 }
                 if (mode == 2) continue;
             }
-            for (int slab = 0; slab < SLABS; ++slab) {
-                const int m0 = slab * MC;
-                for (int tid = 0; tid < THREADS; ++tid) {
-                    const int half = tid >= NF ? 1 : 0, rtid = tid - half * NF;
-                    p4_row<HC>(ws.data() + half * HC * CS, rowmap[rtid], items + rptr[rtid], rptr[rtid + 1] - rptr[rtid], tw,
-                               m0 + half * HC, pc.data());
-                }
-                for (int tid = 0; tid < THREADS; ++tid)
-                    if ((tid & 15) < 14) inv_s1_load(ws.data() + (tid >> 4) * CS, tid & 15, tw2, A(tid));
-                for (int tid = 0; tid < THREADS; ++tid)
-                    if ((tid & 15) < 14) inv_s1_store(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
-                for (int tid = 0; tid < THREADS; ++tid) {
-                    const int l16 = tid & 15, col = tid >> 4;
-                    const size_t g = img + (size_t)(m0 + col) * NF + l16;
-                    float2(&a)[16] = A(tid);
-                    inv_s2_regs(ws.data() + col * CS, l16, a);
-                    for (int d = 0; d < 14; ++d) {
-                        float ore, oim;
-                        if (mode == 0) {
-                            ore = v[g + 16 * d] + a[d].x;
-                            oim = a[d].y;
-                        } else if (mode == 1) {
-                            ore = in_re[g + 16 * d] + a[d].x;
-                            oim = (in_im ? in_im[g + 16 * d] : 0.f) + a[d].y;
-                        } else {
-                            ore = a[d].x;
-                            oim = a[d].y;
+            for (int g = 0; g < G; ++g) {  // one adjoint CTA
+                std::vector<float2> ws((size_t)MC * CS, float2{0, 0});
+                std::vector<float2> ovf((size_t)std::max(t.n_ovf, 1) * OVF_STRIDE, float2{0, 0});
+                for (int sl = 0; sl < SPC; ++sl) {
+                    const int m0 = (g * SPC + sl) * MC;
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        const int k1row = (int)(itA[tid] & 0xffu), cnt = (int)((itA[tid] >> 8) & 0xffu), slot = (int)(itB[tid] & 0xffu);
+                        const int zrow = (int)(itB[tid] >> 24);
+                        if (k1row != 255) {
+                            float2 SP[NP_STREAM], SM[NP_STREAM];
+                            p4_item_partial(SP, SM, ent + (itA[tid] >> 16), cnt, tw448, m0, cvec.data());
+                            if (slot == 0) p4_item_store(ws.data(), k1row, SP, SM);
+                            else p4_item_spill(ovf.data() + (size_t)(slot - 1) * OVF_STRIDE, SP, SM);
                         }
-                        out_re[g + 16 * d] = ore;
-                        out_im[g + 16 * d] = oim;
-                        lmin = fminf(lmin, ore);
-                        lmax = fmaxf(lmax, ore);
+                        if (zrow != 255) p4_zero_row(ws.data(), zrow);
+                    }
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        const int k1row = (int)(itA[tid] & 0xffu), slot = (int)(itB[tid] & 0xffu);
+                        const int novf = (int)((itB[tid] >> 8) & 0xffu), ovf0 = (int)((itB[tid] >> 16) & 0xffu);
+                        if (k1row != 255 && slot == 0 && novf) p4_row_add_overflow(ws.data(), k1row, ovf.data() + (size_t)ovf0 * OVF_STRIDE, novf);
+                    }
+                    for (int tid = 0; tid < THREADS; ++tid)
+                        if ((tid & 15) < 14) inv_s1_load(ws.data() + (tid >> 4) * CS, tid & 15, tw2, A(tid));
+                    for (int tid = 0; tid < THREADS; ++tid)
+                        if ((tid & 15) < 14) inv_s1_store(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        const int l16 = tid & 15, col = tid >> 4;
+                        const size_t gi = img + (size_t)(m0 + col) * NF + l16;
+                        float2(&a)[16] = A(tid);
+                        inv_s2_regs(ws.data() + col * CS, l16, a);
+                        for (int d = 0; d < 14; ++d) {
+                            float ore, oim;
+                            if (mode == 0) {
+                                ore = v[gi + 16 * d] + a[d].x;
+                                oim = a[d].y;
+                            } else if (mode == 1) {
+                                ore = in_re[gi + 16 * d] + a[d].x;
+                                oim = (in_im ? in_im[gi + 16 * d] : 0.f) + a[d].y;
+                            } else {
+                                ore = a[d].x;
+                                oim = a[d].y;
+                            }
+                            out_re[gi + 16 * d] = ore;
+                            out_im[gi + 16 * d] = oim;
+                            lmin = fminf(lmin, ore);
+                            lmax = fmaxf(lmax, ore);
+                        }
                     }
                 }
             }
@@ -277,7 +300,7 @@ int k1emu_run(int mode, int mc, int pattern, double arg, int C, int S, const flo
     optab::K1Tables t;
     optab::build_k1_tables(NF, frames, t);
     if (mc == 0) {  // streaming kernel
-        if (t.max_row > RMAX_STREAM) return -1;
+        if (!t.stream_ok) return -1;
         emulate_stream(mode, C, S, t, in_re, in_im, v, y, rho, out_re, out_im, y_out, minmax);
         return t.nmeas;
     }

@@ -77,18 +77,113 @@ struct K1Tables {
     std::vector<uint32_t> p4tab;      // [C][8][p4_len] flat work lists of the sparse inverse pass (see build_k1_tables)
     int p4_len = 0;
     std::vector<float> tw;            // [224][2]
-    // streaming kernel (xupdate_stream.cu): the sparse m-direction sums are evaluated per k-space row k1, one thread per row
-    std::vector<uint8_t> rowmap;      // [C][N]   row k1 owned by thread tid
-    std::vector<uint16_t> row_ptr;    // [C][N+1] offsets (relative to the frame) of thread tid's samples in `items`
-    std::vector<uint32_t> items;      // [nmeas]  j | k2 << 16, frame-major, grouped by owning thread
+    // streaming kernel (xupdate_stream.cu): work items of the sparse m-direction sums (see build_stream_tables)
+    bool stream_ok = false;           // false: some frame needs more than 224 items / too many overflow partials
+    std::vector<uint32_t> itA;        // [C][N] k1 | cnt << 8 | start << 16   (k1 == 255: thread has no item)
+    std::vector<uint32_t> itB;        // [C][N] slot | novf << 8 | ovf0 << 16 | zrow << 24   (zrow == 255: none)
+    std::vector<uint32_t> ent;        // [nmeas] j | k2 << 16, frame-major, grouped by item
+    int n_ovf = 0;                    // largest number of overflow partials in one frame
     int max_row = 0;                  // largest number of samples in one row of one frame
     std::vector<float> tw2;           // [16][16][2]  e^{-2 pi i (i j) / N}
+    std::vector<float> tw448;         // [2N][2]      e^{-2 pi i t / (2N)}
 };
 
 constexpr int K1_PHASES = 8;          // row phases of the sparse inverse pass = THREADS / MC of the kernel
 // p4tab entry: k2 | k1 << 8 | j << 16 | last_of_row << 31; j == ns_max addresses a zero coefficient (empty rows, padding)
 static inline uint32_t p4_entry(int k2, int k1, int j, bool last) {
     return (uint32_t)k2 | ((uint32_t)k1 << 8) | ((uint32_t)j << 16) | (last ? 0x80000000u : 0u);
+}
+
+
+constexpr int STREAM_QMAX = 24;      // == k1::QMAX_STREAM
+constexpr int STREAM_OVF_MAX = 96;   // == k1::OVF_MAX_STREAM
+
+// Work items of the streaming kernel.  The samples of a k-space row k1 are cut into chunks of at most Q samples (Q = the
+// smallest value for which the frame needs no more than N items, so a thread never carries more than one); the row's first
+// chunk is its PRIMARY item (it writes the row in the inverse pass), the others are OVERFLOW items whose partial sums go
+// through numbered shared-memory slots and are added by the primary in slot order (deterministic, no atomics).  Rows
+// without samples are zero-filled by a thread that is handed the row as a side duty.  Lane placement: thread 16 h + l takes
+// an item of residue class l (k1 = l mod 16) whenever one is left, heaviest first, so the 16 lanes of a half-warp address 16
+// different bank pairs in the [column][k1] workspace and the items of a warp carry similar sample counts.
+static inline void build_stream_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t) {
+    t.stream_ok = (N % 16 == 0) && N <= 254;
+    t.itA.assign((size_t)t.C * N, 255u);
+    t.itB.assign((size_t)t.C * N, 255u << 24);
+    t.ent.assign(std::max(t.nmeas, 1), 0);
+    t.n_ovf = 0;
+    t.max_row = 0;
+    if (!t.stream_ok) return;
+    struct Item { int k1, first, cnt, chunk, nchunks, ovf0; };
+    for (int c = 0; c < t.C; ++c) {
+        const auto& f = frames[c];
+        std::vector<std::vector<uint32_t>> rows(N);
+        for (int j = 0; j < (int)f.size(); ++j) rows[f[j] % N].push_back((uint32_t)j | ((uint32_t)(f[j] / N) << 16));
+        for (int k = 0; k < N; ++k) t.max_row = std::max(t.max_row, (int)rows[k].size());
+        int Q = 0;
+        for (int q = 1; q <= STREAM_QMAX && !Q; ++q) {
+            int items = 0, ovf = 0;
+            for (int k = 0; k < N; ++k) {
+                int n = ((int)rows[k].size() + q - 1) / q;
+                items += n;
+                ovf += std::max(0, n - 1);
+            }
+            if (items <= N && ovf <= STREAM_OVF_MAX && ovf <= 254) Q = q;
+        }
+        if (!Q) {
+            t.stream_ok = false;
+            return;
+        }
+        std::vector<Item> items;
+        int slots = 0;
+        for (int k = 0; k < N; ++k) {
+            const int sz = (int)rows[k].size();
+            if (!sz) continue;
+            const int n = (sz + Q - 1) / Q;
+            int first = 0;
+            for (int ch = 0; ch < n; ++ch) {
+                const int cnt = sz / n + (ch < sz % n ? 1 : 0);  // even split
+                items.push_back({k, first, cnt, ch, n, slots});
+                first += cnt;
+            }
+            slots += n - 1;
+        }
+        t.n_ovf = std::max(t.n_ovf, slots);
+        // lane placement
+        std::vector<std::vector<int>> bucket(16);
+        for (int i = 0; i < (int)items.size(); ++i) bucket[items[i].k1 % 16].push_back(i);
+        for (auto& b : bucket) std::stable_sort(b.begin(), b.end(), [&](int a, int b2) { return items[a].cnt > items[b2].cnt; });
+        std::vector<int> place(N, -1), left;
+        const int H = N / 16;
+        for (int l = 0; l < 16; ++l)
+            for (int h = 0; h < (int)bucket[l].size(); ++h) {
+                if (h < H) place[16 * h + l] = bucket[l][h];
+                else left.push_back(bucket[l][h]);
+            }
+        std::stable_sort(left.begin(), left.end(), [&](int a, int b2) { return items[a].cnt > items[b2].cnt; });
+        for (int tid = 0, q = 0; tid < N && q < (int)left.size(); ++tid)
+            if (place[tid] < 0) place[tid] = left[q++];
+        // zero-fill duties: rows without samples, handed out from the last thread backwards (the lightest items)
+        std::vector<int> zrow(N, 255);
+        {
+            int tid = N - 1;
+            for (int k = 0; k < N; ++k)
+                if (rows[k].empty()) zrow[tid--] = k;
+        }
+        size_t pos = 0;
+        for (int tid = 0; tid < N; ++tid) {
+            uint32_t A = 255u, B = (uint32_t)zrow[tid] << 24;
+            if (place[tid] >= 0) {
+                const Item& it = items[place[tid]];
+                A = (uint32_t)it.k1 | ((uint32_t)it.cnt << 8) | ((uint32_t)pos << 16);
+                const int slot = it.chunk == 0 ? 0 : it.ovf0 + it.chunk;  // overflow slots are numbered from 1
+                const int novf = it.chunk == 0 ? it.nchunks - 1 : 0;
+                B |= (uint32_t)slot | ((uint32_t)novf << 8) | ((uint32_t)it.ovf0 << 16);
+                for (int q = 0; q < it.cnt; ++q) t.ent[t.frame_ptr[c] + pos++] = rows[it.k1][it.first + q];
+            }
+            t.itA[(size_t)c * N + tid] = A;
+            t.itB[(size_t)c * N + tid] = B;
+        }
+    }
 }
 
 static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t) {
@@ -136,36 +231,14 @@ static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>
     for (int c = 0; c < t.C; ++c)
         for (int ph = 0; ph < K1_PHASES; ++ph)
             std::copy(lists[c][ph].begin(), lists[c][ph].end(), t.p4tab.begin() + ((size_t)c * K1_PHASES + ph) * t.p4_len);
-    // Row tables of the streaming kernel.  Thread tid = 16 h + l owns the row of residue class l (k1 = l mod 16) that has
-    // the h-th most samples in its class: the 16 lanes of a half-warp then address 16 different bank pairs (conflict-free
-    // 64-bit shared-memory accesses to [mm][k1]) and the rows of a warp carry similar sample counts (little divergence).
-    t.rowmap.assign((size_t)t.C * N, 0);
-    t.row_ptr.assign((size_t)t.C * (N + 1), 0);
-    t.items.assign(std::max(t.nmeas, 1), 0);
-    t.max_row = 0;
-    if (N % 16 == 0) {
-        for (int c = 0; c < t.C; ++c) {
-            const auto& f = frames[c];
-            std::vector<std::vector<uint32_t>> rows(N);
-            for (int j = 0; j < (int)f.size(); ++j) rows[f[j] % N].push_back((uint32_t)j | ((uint32_t)(f[j] / N) << 16));
-            for (int k = 0; k < N; ++k) t.max_row = std::max(t.max_row, (int)rows[k].size());
-            const int H = N / 16;
-            for (int l = 0; l < 16; ++l) {
-                std::vector<int> cls(H);
-                for (int q = 0; q < H; ++q) cls[q] = l + 16 * q;
-                std::stable_sort(cls.begin(), cls.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
-                for (int h = 0; h < H; ++h) t.rowmap[(size_t)c * N + 16 * h + l] = (uint8_t)cls[h];
-            }
-            size_t pos = 0;
-            for (int tid = 0; tid < N; ++tid) {
-                t.row_ptr[(size_t)c * (N + 1) + tid] = (uint16_t)pos;
-                for (uint32_t e : rows[t.rowmap[(size_t)c * N + tid]]) t.items[t.frame_ptr[c] + pos++] = e;
-            }
-            t.row_ptr[(size_t)c * (N + 1) + N] = (uint16_t)pos;
-        }
-    }
+    build_stream_tables(N, frames, t);
     t.tw.resize(2 * N);
     const double PI = 3.14159265358979323846;
+    t.tw448.resize(4 * N);
+    for (int i = 0; i < 2 * N; ++i) {
+        t.tw448[2 * i] = (float)cos(-PI * i / N);
+        t.tw448[2 * i + 1] = (float)sin(-PI * i / N);
+    }
     t.tw2.resize(2 * 256);
     for (int i = 0; i < 16; ++i)
         for (int j = 0; j < 16; ++j) {

@@ -236,12 +236,14 @@ struct qmri_op {
     uint16_t* d_samp = nullptr;
     uint32_t* d_p4tab = nullptr;
     float2* d_tw2 = nullptr;
-    uint8_t* d_rowmap = nullptr;
-    uint16_t* d_row_ptr = nullptr;
-    uint32_t* d_items = nullptr;
+    float2* d_tw448 = nullptr;
+    uint32_t* d_itA = nullptr;
+    uint32_t* d_itB = nullptr;
+    uint32_t* d_ent = nullptr;
     int k1_kernel = 0;  // 0 = choose by batch size, 1 = cluster kernel, 2 = streaming kernel (QMRI_K1_KERNEL=cluster|stream)
     // scratch for the host entry points
     DevBuf stage, a_re, a_im, b_re, b_im, c_re, c_im, ybuf, mm_ord, mm_f;
+    DevBuf k1_part, k1_cbuf;  // streaming x-update: partial sample sums / solved samples
     size_t plane() const { return (size_t)N * M * C; }
 };
 
@@ -283,9 +285,10 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     r |= dev_alloc(&op->d_samp, nm);
     r |= dev_alloc(&op->d_p4tab, std::max<size_t>(t.p4tab.size(), 1));
     r |= dev_alloc(&op->d_tw2, (size_t)256);
-    r |= dev_alloc(&op->d_rowmap, t.rowmap.size());
-    r |= dev_alloc(&op->d_row_ptr, t.row_ptr.size());
-    r |= dev_alloc(&op->d_items, t.items.size());
+    r |= dev_alloc(&op->d_tw448, (size_t)2 * N);
+    r |= dev_alloc(&op->d_itA, t.itA.size());
+    r |= dev_alloc(&op->d_itB, t.itB.size());
+    r |= dev_alloc(&op->d_ent, t.ent.size());
     if (r) {
         qmri_op_destroy(op);
         return QMRI_ENOMEM;
@@ -294,9 +297,10 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     cudaMemcpy(op->d_frame_ptr, t.frame_ptr.data(), sizeof(int) * (C + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_samp, t.samp.data(), sizeof(uint16_t) * t.nmeas, cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_tw2, t.tw2.data(), sizeof(float) * t.tw2.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(op->d_rowmap, t.rowmap.data(), t.rowmap.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(op->d_row_ptr, t.row_ptr.data(), sizeof(uint16_t) * t.row_ptr.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(op->d_items, t.items.data(), sizeof(uint32_t) * t.items.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_tw448, t.tw448.data(), sizeof(float) * t.tw448.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_itA, t.itA.data(), sizeof(uint32_t) * t.itA.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_itB, t.itB.data(), sizeof(uint32_t) * t.itB.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_ent, t.ent.data(), sizeof(uint32_t) * t.ent.size(), cudaMemcpyHostToDevice);
     cudaError_t e = cudaMemcpy(op->d_p4tab, t.p4tab.data(), sizeof(uint32_t) * t.p4tab.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         qmri_op_destroy(op);
@@ -335,9 +339,10 @@ extern "C" int qmri_op_destroy(qmri_op* op) {
     cudaStreamSynchronize(op->ctx->stream);
     cudaFree(op->d_tw); cudaFree(op->d_frame_ptr); cudaFree(op->d_samp);
     cudaFree(op->d_p4tab);
-    cudaFree(op->d_tw2); cudaFree(op->d_rowmap); cudaFree(op->d_row_ptr); cudaFree(op->d_items);
+    cudaFree(op->d_tw2); cudaFree(op->d_tw448); cudaFree(op->d_itA); cudaFree(op->d_itB); cudaFree(op->d_ent);
     op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
     op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
+    op->k1_part.release(); op->k1_cbuf.release();
     delete op;
     return QMRI_OK;
 }
@@ -353,17 +358,26 @@ extern "C" int qmri_op_indices(const qmri_op* op, int32_t* idx, int64_t* frame_p
 // Kernel choice for one x-update launch: the streaming kernel (one CTA per slice-channel, xupdate_stream.cu) once the batch
 // fills the machine, the cluster kernel (eight CTAs per slice-channel, xupdate_kernel.cu) for small batches and for masks
 // with densely sampled k-space rows (EPI lines).  QMRI_K1_KERNEL=cluster|stream forces one (tests, profiling).
-static int k1_dispatch(const qmri_op* op, const K1Params& p, int S) {
+static int k1_dispatch(qmri_op* op, const K1Params& p_in, int S) {
+    K1Params p = p_in;
     qmri_ctx* ctx = op->ctx;
-    const bool can_stream = k1_stream_supported(op->t.max_row, op->t.ns_max);
+    const bool can_stream = op->t.stream_ok;
     bool stream = can_stream && (long long)S * op->C >= K1_STREAM_MIN_CTAS_PER_SM * (long long)ctx->sm_count;
     if (op->k1_kernel == 1) stream = false;
     if (op->k1_kernel == 2) {
         if (!can_stream)
-            return qmri_fail(QMRI_EUNSUPPORTED, "QMRI_K1_KERNEL=stream: a k-space row of this mask holds %d samples (limit %d)", op->t.max_row, 24);
+            return qmri_fail(QMRI_EUNSUPPORTED, "QMRI_K1_KERNEL=stream: this mask does not fit the streaming kernel's work-item tables (densest k-space row: %d samples)", op->t.max_row);
         stream = true;
     }
-    if (stream) return k1_stream_launch(ctx, p, S, op->t.ns_max);
+    if (stream) {
+        p.G = k1_stream_groups(S, op->C, ctx->sm_count);
+        // (re)allocation happens on the first launch of a batch size, i.e. before any CUDA-graph capture of the loop
+        QCHECK(op->k1_part.ensure(k1_stream_part_elems(S, op->C, p.G, op->t.ns_max) * sizeof(float2)));
+        QCHECK(op->k1_cbuf.ensure(k1_stream_cbuf_elems(S, op->C, op->t.ns_max) * sizeof(float2)));
+        p.part = op->k1_part.as<float2>();
+        p.cbuf = op->k1_cbuf.as<float2>();
+        return k1_stream_launch(ctx, p, S, op->t.ns_max);
+    }
     return k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc);
 }
 
@@ -374,9 +388,11 @@ static void k1_fill_tables(const qmri_op* op, K1Params& p) {
     p.p4tab = op->d_p4tab;
     p.p4_len = op->t.p4_len;
     p.tw2 = op->d_tw2;
-    p.rowmap = op->d_rowmap;
-    p.row_ptr = op->d_row_ptr;
-    p.items = op->d_items;
+    p.tw448 = op->d_tw448;
+    p.itA = op->d_itA;
+    p.itB = op->d_itB;
+    p.ent = op->d_ent;
+    p.n_ovf = op->t.n_ovf;
     p.C = op->C;
     p.nmeas = op->t.nmeas;
 }

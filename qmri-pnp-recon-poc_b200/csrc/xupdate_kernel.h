@@ -29,9 +29,15 @@ struct K1Params {
     int p4_len;
     // streaming kernel tables (xupdate_stream.cu; op_tables.h)
     const float2* tw2;       // [16][16] e^{-2 pi i (i j) / 224}
-    const uint8_t* rowmap;   // [C][224] k-space row owned by thread tid
-    const uint16_t* row_ptr; // [C][225] offsets of thread tid's samples in `items`, relative to the frame
-    const uint32_t* items;   // [nmeas] j | k2 << 16, frame-major, grouped by owning thread
+    const float2* tw448;     // [448] e^{-2 pi i t / 448}
+    const uint32_t* itA;     // [C][224] work item of thread tid: k1 | cnt << 8 | start << 16
+    const uint32_t* itB;     // [C][224] slot | novf << 8 | ovf0 << 16 | zrow << 24
+    const uint32_t* ent;     // [nmeas] j | k2 << 16, frame-major, grouped by item
+    int n_ovf;               // overflow partials per frame (sizes the shared-memory slots)
+    float2* part;            // scratch [S][C][G][ns_max] partial sample sums of the forward kernel
+    float2* cbuf;            // scratch [S][C][ns_max]    c = (y - A z) / (1 + rho)
+    int G;                   // slab groups (CTAs) per image: 2, 4, 8 or 16
+    int slabs_per_cta;       // 16 / G (set by k1_stream_launch)
     int C;
     int nmeas;
     int ns_max;              // largest per-frame sample count (sizes the shared-memory tables; set by k1_launch)
@@ -41,7 +47,9 @@ struct K1Params {
 
 int k1_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max, int mc);
 constexpr int K1_STREAM_MIN_CTAS_PER_SM = 2;  // use the streaming kernel from S * C >= 2 * SM count on
-// streaming variant: one CTA per (slice, channel); needs <= RMAX_STREAM samples per k-space row
-bool k1_stream_supported(int max_row, int ns_max);
+// streaming variant: one CTA per (slice, channel); needs K1Tables::stream_ok
+int k1_stream_groups(int S, int C, int sm_count);
+size_t k1_stream_part_elems(int S, int C, int G, int ns_max);
+size_t k1_stream_cbuf_elems(int S, int C, int ns_max);
 int k1_stream_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max);
 int k1_minmax_init(qmri_ctx* ctx, int* minmax, int S);

@@ -224,7 +224,8 @@ QHD void sparse_idft_flat(float2* col, const float2* c, const float2* twp, const
 //    twiddle (t <- t * e^{-+2 pi i k2 / 224}), so the inner loops touch no shared memory.
 // tw2[i][j] = e^{-2 pi i (i j) / 224}, i, j < 16: stage twiddles, lanes contiguous in j.
 // =====================================================================================
-constexpr int RMAX_STREAM = 24;  // rows with more samples than this need the cluster kernel (e.g. EPI lines)
+constexpr int QMAX_STREAM = 24;      // most samples one work item may carry
+constexpr int OVF_MAX_STREAM = 96;   // most overflow partials (row chunks beyond the first) per frame
 
 // forward stage 1 on register inputs: a[n1] = x[16 n1 + n2]
 QHD void fwd_s1_regs(float2 (&a)[16], int n2, const float2* tw2) {
@@ -256,54 +257,118 @@ QHD void inv_s2_regs(const float2* col, int c, float2 (&x)[16]) {
     for (int d = 0; d < 14; ++d) x[d] = cswap(x[d]);
 }
 
-// sampled forward DFT along m for the samples of one row k1: items[q] = j | k2 << 16.
-// pc[j] += sum_mm T[mm][k1] e^{-2 pi i k2 (m0 + mm) / 224}
-template <int MC>
-QHD void p3_row(const float2* ws, int k1, const uint32_t* items, int cnt, const float2* tw, int m0, float2* pc) {
+// ---- sparse m-direction sums of the streaming kernel -------------------------------------------------
+// Work item = (k-space row k1, up to Q of the row's samples, one half slab of HC = 14 columns); ent[q] = j | k2 << 16.
+// The 14 columns are taken in pairs mirrored about the centre of the half slab, columns 6 - d' and 7 + d' (d = d' + 1/2):
+//   e^{-i phi (base +- d)} = tc * r_d^{+-1},   tc = e^{-i phi base} (base = m0 + 6.5),   r_d = e^{-i phi d},   phi = 2 pi k2 / 224
+// so with P_d = T[7+d'] + T[6-d'], M_d = T[7+d'] - T[6-d'] (formed once per item) a sample costs 4 FMAs and one twiddle
+// rotation per column PAIR.  tw448[x] = e^{-2 pi i x / 448} supplies the half-integer phases.
+constexpr int HC_STREAM = 14;
+constexpr int NP_STREAM = 7;      // column pairs per half slab
+constexpr int OVF_STRIDE = 15;    // float2 per overflow partial (14 used; odd stride keeps the lanes on different banks)
+
+// forward: pc[j] += sum_mm T[mm][k1] e^{-2 pi i k2 (m0 + mm) / 224} over the 14 columns starting at ws (m0 = first column)
+QHD void p3_item(const float2* ws, int k1, const uint32_t* ent, int cnt, const float2* tw448, int m0, float2* pc) {
     if (cnt == 0) return;
-    float2 T[MC];
+    float2 Pp[NP_STREAM], Mm[NP_STREAM];
 #pragma unroll
-    for (int mm = 0; mm < MC; ++mm) T[mm] = ws[mm * CS + k1];
+    for (int d = 0; d < NP_STREAM; ++d) {
+        const float2 tp = ws[(7 + d) * CS + k1], tm = ws[(6 - d) * CS + k1];
+        Pp[d] = cadd(tp, tm);
+        Mm[d] = csub(tp, tm);
+    }
     for (int q = 0; q < cnt; ++q) {
-        const uint32_t en = items[q];
+        const uint32_t en = ent[q];
         const int k2 = (int)(en >> 16), j = (int)(en & 0xffffu);
-        float2 t = tw[(k2 * m0) % NF];
-        const float2 st = tw[k2];
+        float2 r = tw448[k2];          // r_{1/2}
+        const float2 st = tw448[2 * k2];  // e^{-i phi}
+        const float2 tc = tw448[(k2 * (2 * m0 + 13)) % (2 * NF)];
         float ax = 0.f, ay = 0.f;
 #pragma unroll
-        for (int mm = 0; mm < MC; ++mm) {
-            ax = fmaf(T[mm].x, t.x, ax);
-            ax = fmaf(-T[mm].y, t.y, ax);
-            ay = fmaf(T[mm].x, t.y, ay);
-            ay = fmaf(T[mm].y, t.x, ay);
-            t = cmul(t, st);
+        for (int d = 0; d < NP_STREAM; ++d) {
+            ax = fmaf(r.x, Pp[d].x, ax);
+            ax = fmaf(-r.y, Mm[d].y, ax);
+            ay = fmaf(r.x, Pp[d].y, ay);
+            ay = fmaf(r.y, Mm[d].x, ay);
+            r = cmul(r, st);
         }
-        float2 o = pc[j];
-        pc[j] = make_float2(o.x + ax, o.y + ay);
+        const float2 a = cmul(make_float2(ax, ay), tc);
+        const float2 o = pc[j];
+        pc[j] = make_float2(o.x + a.x, o.y + a.y);
     }
 }
 
-// sparse inverse DFT along m for one row k1:  U[mm][k1] = sum_j c_j e^{+2 pi i k2_j (m0 + mm) / 224}
-template <int MC>
-QHD void p4_row(float2* ws, int k1, const uint32_t* items, int cnt, const float2* tw, int m0, const float2* pc) {
-    float2 U[MC];
+// inverse, step 1: partial sums of  U[mm] = sum_j c_j e^{+2 pi i k2_j (m0 + mm) / 224}  in the (P, M) basis:
+//   SP_d = sum_j u_j Re r_d,  SM_d = sum_j u_j Im r_d,  u_j = c_j conj(tc_j)
+QHD void p4_item_partial(float2 (&SP)[NP_STREAM], float2 (&SM)[NP_STREAM], const uint32_t* ent, int cnt, const float2* tw448, int m0,
+                         const float2* pc) {
 #pragma unroll
-    for (int mm = 0; mm < MC; ++mm) U[mm] = make_float2(0.f, 0.f);
+    for (int d = 0; d < NP_STREAM; ++d) {
+        SP[d] = make_float2(0.f, 0.f);
+        SM[d] = make_float2(0.f, 0.f);
+    }
     for (int q = 0; q < cnt; ++q) {
-        const uint32_t en = items[q];
+        const uint32_t en = ent[q];
         const int k2 = (int)(en >> 16), j = (int)(en & 0xffffu);
-        const float2 s0 = tw[(k2 * m0) % NF], s1 = tw[k2];
-        const float2 st = make_float2(s1.x, -s1.y);
-        float2 t = cmul(pc[j], make_float2(s0.x, -s0.y));
+        float2 r = tw448[k2];
+        const float2 st = tw448[2 * k2];
+        const float2 tc = tw448[(k2 * (2 * m0 + 13)) % (2 * NF)];
+        const float2 u = cmul(pc[j], make_float2(tc.x, -tc.y));
 #pragma unroll
-        for (int mm = 0; mm < MC; ++mm) {
-            U[mm].x += t.x;
-            U[mm].y += t.y;
-            t = cmul(t, st);
+        for (int d = 0; d < NP_STREAM; ++d) {
+            SP[d].x = fmaf(u.x, r.x, SP[d].x);
+            SP[d].y = fmaf(u.y, r.x, SP[d].y);
+            SM[d].x = fmaf(u.x, r.y, SM[d].x);
+            SM[d].y = fmaf(u.y, r.y, SM[d].y);
+            r = cmul(r, st);
+        }
+    }
+}
+// inverse, step 2: a primary item leaves the (P, M) basis and writes its row ...
+QHD void p4_item_store(float2* ws, int k1, const float2 (&SP)[NP_STREAM], const float2 (&SM)[NP_STREAM]) {
+#pragma unroll
+    for (int d = 0; d < NP_STREAM; ++d) {
+        ws[(7 + d) * CS + k1] = make_float2(SP[d].x + SM[d].y, SP[d].y - SM[d].x);   // u conj(r)
+        ws[(6 - d) * CS + k1] = make_float2(SP[d].x - SM[d].y, SP[d].y + SM[d].x);   // u r
+    }
+}
+// ... and, after a barrier, adds the row's overflow partials in slot order (consecutive slots are OVF_STRIDE apart)
+QHD void p4_row_add_overflow(float2* ws, int k1, const float2* ovf, int novf) {
+    float2 SP[NP_STREAM], SM[NP_STREAM];
+#pragma unroll
+    for (int d = 0; d < NP_STREAM; ++d) {
+        SP[d] = ovf[d];
+        SM[d] = ovf[NP_STREAM + d];
+    }
+    for (int i = 1; i < novf; ++i) {
+        const float2* o = ovf + (size_t)i * OVF_STRIDE;
+#pragma unroll
+        for (int d = 0; d < NP_STREAM; ++d) {
+            const float2 a = o[d], b = o[NP_STREAM + d];
+            SP[d].x += a.x; SP[d].y += a.y;
+            SM[d].x += b.x; SM[d].y += b.y;
         }
     }
 #pragma unroll
-    for (int mm = 0; mm < MC; ++mm) ws[mm * CS + k1] = U[mm];
+    for (int d = 0; d < NP_STREAM; ++d) {
+        float2 up = ws[(7 + d) * CS + k1], um = ws[(6 - d) * CS + k1];
+        ws[(7 + d) * CS + k1] = make_float2(up.x + (SP[d].x + SM[d].y), up.y + (SP[d].y - SM[d].x));
+        ws[(6 - d) * CS + k1] = make_float2(um.x + (SP[d].x - SM[d].y), um.y + (SP[d].y + SM[d].x));
+    }
 }
+QHD void p4_item_spill(float2* o, const float2 (&SP)[NP_STREAM], const float2 (&SM)[NP_STREAM]) {
+#pragma unroll
+    for (int d = 0; d < NP_STREAM; ++d) {
+        o[d] = SP[d];
+        o[NP_STREAM + d] = SM[d];
+    }
+}
+QHD void p4_zero_row(float2* ws, int k1) {
+#pragma unroll
+    for (int mm = 0; mm < HC_STREAM; ++mm) ws[mm * CS + k1] = make_float2(0.f, 0.f);
+}
+
+// item table words (op_tables.h): A = k1 | cnt << 8 | start << 16 (k1 == 255: no item);
+//                                 B = slot | novf << 8 | ovf0 << 16 | zrow << 24 (slot 0: primary; zrow == 255: none)
 
 }  // namespace k1

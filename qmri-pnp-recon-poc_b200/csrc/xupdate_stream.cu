@@ -6,19 +6,21 @@
 // with F.forward / F.adjoint of main_recon_tsmis_FFT.m:228-229 - in the closed form
 //   x = z + A^H (y - A z) / (1 + rho)          (A A^H = I, see xupdate_phases.cuh).
 //
-// Work decomposition: ONE CTA per (slice, channel).  The CTA walks the eight 28-column slabs of the
-// 224 x 224 image twice:
-//   pass A  slab -> registers -> FFT along n -> sampled DFT along m, accumulated into the <= ~700 sample
-//           values of the channel (shared memory);       then the data-consistency solve on those samples;
-//   pass B  sparse inverse DFT along m -> inverse FFT along n -> registers -> w' = v + corr -> global.
-// Compared with the cluster kernel (xupdate_kernel.cu) there is no cluster barrier and no DSMEM exchange,
-// the operator tables are read once per image instead of once per slab, and the shared-memory traffic is
-// about a third: the first / last FFT stage works on registers filled from / drained to global memory,
-// and the sparse sums keep a k-space row in registers and rotate the twiddle instead of looking it up.
-// HBM traffic per pixel-channel: read w (8 B) + v (4 B) in pass A, write w' (8 B) in pass B; pass B reads
-// v a second time (4 B), normally from L2 - the CTA touched it a few tens of microseconds earlier.
-// The kernel needs every k-space row of a frame to hold at most RMAX_STREAM samples (true for the spiral
-// masks); line-sampled masks (EPI) and small slice batches stay on the cluster kernel.
+// The cluster kernel (xupdate_kernel.cu) keeps a whole (slice, channel) image on chip in the shared memory
+// of eight CTAs; that is the right shape for a handful of slices, but it is bound by shared-memory traffic,
+// cluster barriers and the sparse-DFT table walks.  For batches that fill the machine the update is split
+// at its only global dependency - the <= ~700 sampled k-space values of a channel:
+//   stream_fwd_kernel     grid (G, C, S): 224 / G columns of one image, 14 at a time:  global -> registers ->
+//                         FFT along n -> sampled DFT along m;  partial sample sums -> `part` (5 KB per CTA)
+//   stream_solve_kernel   grid (C, S): adds the G partials in a fixed order, c = (y - A z) / (1 + rho)
+//   stream_adj_kernel     grid (G, C, S): sparse inverse DFT along m -> inverse FFT along n -> registers ->
+//                         w' = v + corr (+ x on the last iteration) -> global; per-slice min / max
+// No cluster, no DSMEM, CTAs of 224 threads at four per SM, work items small enough that the last wave is
+// short.  The first / last FFT stage works on registers filled from / drained to global memory and the
+// sparse sums run on per-row work items with rotating twiddles (xupdate_phases.cuh), so the shared-memory
+// traffic is about a third of the cluster kernel's.  HBM traffic per pixel-channel: read w (8 B) + v (4 B)
+// in the forward kernel, read v again (4 B) and write w' (8 B) in the adjoint kernel = 24 B against the
+// 20 B of the single-pass formulation; `part` and `c` add < 2 %.
 #include <math.h>
 
 #include "common.cuh"
@@ -29,127 +31,191 @@ using namespace k1;
 
 namespace {
 
-constexpr int MC = 28;                // slab width (columns)
-constexpr int THREADS = 16 * MC;      // 448: 28 column FFTs x 16 lanes; in the sparse passes thread = (k-space row, half of the slab)
-constexpr int SLABS = NF / MC;        // 8
-constexpr int HC = MC / 2;            // 14 columns per half slab
+constexpr int MC = HC_STREAM;         // 14 columns per slab
+constexpr int THREADS = 16 * MC;      // 224: 14 column FFTs x 16 lanes; in the sparse passes one thread per work item
+constexpr int SLABS = NF / MC;        // 16 slabs per image
 
 __device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+struct Item {
+    int k1, cnt, start, slot, novf, ovf0, zrow;
+};
+__device__ __forceinline__ Item decode_item(uint32_t A, uint32_t B) {
+    Item it;
+    it.k1 = (int)(A & 0xffu);            // 255: no item
+    it.cnt = (int)((A >> 8) & 0xffu);
+    it.start = (int)(A >> 16);
+    it.slot = (int)(B & 0xffu);          // 0: primary item of its row
+    it.novf = (int)((B >> 8) & 0xffu);
+    it.ovf0 = (int)((B >> 16) & 0xffu);
+    it.zrow = (int)(B >> 24);            // 255: no zero-fill duty
+    return it;
+}
+
+// ---------------- forward: partial sums of A z over a group of slabs -------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 2) xupdate_stream_kernel(K1Params p) {
+__global__ void __launch_bounds__(THREADS, 4) stream_fwd_kernel(K1Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* ws = reinterpret_cast<float2*>(smem_raw);                  // [MC][CS] slab workspace
-    float2* tw = ws + MC * CS;                                         // [224]
-    float2* tw2 = tw + NF;                                             // [16][16]
-    float2* pc = tw2 + 256;                                            // [2][ns_max] sample accumulators (one per half slab), then c in [0]
-    uint32_t* s_items = reinterpret_cast<uint32_t*>(pc + 2 * p.ns_max);  // [ns_max]
-    uint16_t* s_rptr = reinterpret_cast<uint16_t*>(s_items + p.ns_max);  // [225]
-    __shared__ float red_min[THREADS / 32], red_max[THREADS / 32];
+    float2* tw2 = ws + MC * CS;                                        // [16][16]
+    float2* tw448 = tw2 + 256;                                         // [448]
+    float2* pc = tw448 + 2 * NF;                                       // [ns_max] sample accumulators
+    uint32_t* s_ent = reinterpret_cast<uint32_t*>(pc + p.ns_max);      // [ns_max]
 
     const int tid = threadIdx.x;
-    const int c = blockIdx.x;
-    const int s = blockIdx.y;
+    const int g = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
     const int f0 = p.frame_ptr[c];
     const int ns = p.frame_ptr[c + 1] - f0;
     const size_t img = ((size_t)s * p.C + c) * (size_t)(NF * NF);
-    const float inv_n = 1.0f / (float)NF;  // unitary scaling 1/sqrt(N*M), once per transform direction
 
-    for (int i = tid; i < NF; i += THREADS) tw[i] = p.tw[i];
     for (int i = tid; i < 256; i += THREADS) tw2[i] = p.tw2[i];
+    for (int i = tid; i < 2 * NF; i += THREADS) tw448[i] = p.tw448[i];
     for (int i = tid; i < ns; i += THREADS) {
-        s_items[i] = p.items[f0 + i];
-        if (MODE == K1_ADJOINT) {
-            const float2 y = p.y[(size_t)s * p.nmeas + f0 + i];
-            pc[i] = make_float2(y.x * inv_n, y.y * inv_n);
-        } else {
-            pc[i] = make_float2(0.f, 0.f);
-            pc[p.ns_max + i] = make_float2(0.f, 0.f);
-        }
+        s_ent[i] = p.ent[f0 + i];
+        pc[i] = make_float2(0.f, 0.f);
     }
-    for (int i = tid; i <= NF; i += THREADS) s_rptr[i] = p.row_ptr[(size_t)c * (NF + 1) + i];
-    const int half = tid >= NF ? 1 : 0;   // warps 0-6: columns 0-13 of the slab, warps 7-13: columns 14-27
-    const int rtid = tid - half * NF;
-    const int k1row = p.rowmap[(size_t)c * NF + rtid];
-    __syncthreads();
-    const uint32_t* my_items = s_items + s_rptr[rtid];
-    const int my_cnt = s_rptr[rtid + 1] - s_rptr[rtid];
+    const uint32_t itA = p.itA[(size_t)c * NF + tid];
     const int l16 = tid & 15;
     const int col = tid >> 4;
+    float2* colp = ws + col * CS;
+    __syncthreads();
 
-    // ---------------- pass A: forward transform sampled on the mask -------------------------------------
-    if (MODE != K1_ADJOINT) {
+    const int slab0 = g * p.slabs_per_cta;
 #pragma unroll 1
-        for (int slab = 0; slab < SLABS; ++slab) {
-            const int m0 = slab * MC;
-            {
-                const size_t g = img + (size_t)(m0 + col) * NF + l16;
-                float2 a[16];
-                if (MODE == K1_ADMM) {  // z = 2 v - w
-                    float wr[14], wi[14], vv[14];
+    for (int sl = 0; sl < p.slabs_per_cta; ++sl) {
+        const int m0 = (slab0 + sl) * MC;
+        {
+            const size_t gi = img + (size_t)(m0 + col) * NF + l16;
+            float2 a[16];
+            if (MODE == K1_ADMM) {  // z = 2 v - w
+                float wr[14], wi[14], vv[14];
 #pragma unroll
-                    for (int n1 = 0; n1 < 14; ++n1) {
-                        wr[n1] = __ldcs(p.in_re + g + 16 * n1);
-                        wi[n1] = __ldcs(p.in_im + g + 16 * n1);
-                        vv[n1] = __ldg(p.v + g + 16 * n1);
-                    }
-#pragma unroll
-                    for (int n1 = 0; n1 < 14; ++n1) a[n1] = make_float2(2.f * vv[n1] - wr[n1], -wi[n1]);
-                } else {
-#pragma unroll
-                    for (int n1 = 0; n1 < 14; ++n1)
-                        a[n1] = make_float2(__ldcs(p.in_re + g + 16 * n1), p.in_im ? __ldcs(p.in_im + g + 16 * n1) : 0.f);
+                for (int n1 = 0; n1 < 14; ++n1) {
+                    wr[n1] = __ldcs(p.in_re + gi + 16 * n1);
+                    wi[n1] = __ldcs(p.in_im + gi + 16 * n1);
+                    vv[n1] = __ldg(p.v + gi + 16 * n1);
                 }
-                float2* colp = ws + col * CS;
-                fwd_s1_regs(a, l16, tw2);
-                fft_s1_store(colp, l16, a);
-                __syncwarp();
-                if (l16 < 14) fft_s2_load(colp, l16, a);
-                __syncwarp();
-                if (l16 < 14) fft_s2_store<false>(colp, l16, a);
-            }
-            __syncthreads();
-            p3_row<HC>(ws + half * HC * CS, k1row, my_items, my_cnt, tw, m0 + half * HC, pc + half * p.ns_max);
-            __syncthreads();
-        }
-        // data-consistency solve on the samples (each sample is owned by the thread of its row: no race above)
-        for (int j = tid; j < ns; j += THREADS) {
-            const size_t yi = (size_t)s * p.nmeas + f0 + j;
-            const float2 az = make_float2((pc[j].x + pc[p.ns_max + j].x) * inv_n, (pc[j].y + pc[p.ns_max + j].y) * inv_n);
-            if (MODE == K1_FORWARD) {
-                p.y_out[yi] = az;
+#pragma unroll
+                for (int n1 = 0; n1 < 14; ++n1) a[n1] = make_float2(2.f * vv[n1] - wr[n1], -wi[n1]);
             } else {
-                const float2 y = p.y[yi];
-                const float gsc = p.inv_1p_rho * inv_n;  // (y - A z)/(1 + rho), pre-scaled for the inverse transform
-                pc[j] = make_float2((y.x - az.x) * gsc, (y.y - az.y) * gsc);
+#pragma unroll
+                for (int n1 = 0; n1 < 14; ++n1)
+                    a[n1] = make_float2(__ldcs(p.in_re + gi + 16 * n1), p.in_im ? __ldcs(p.in_im + gi + 16 * n1) : 0.f);
             }
+            fwd_s1_regs(a, l16, tw2);
+            fft_s1_store(colp, l16, a);
+            __syncwarp();
+            if (l16 < 14) fft_s2_load(colp, l16, a);
+            __syncwarp();
+            if (l16 < 14) fft_s2_store<false>(colp, l16, a);
         }
-        if (MODE == K1_FORWARD) return;
+        __syncthreads();
+        p3_item(ws, (int)(itA & 0xffu), s_ent + (itA >> 16), (int)((itA >> 8) & 0xffu), tw448, m0, pc);
         __syncthreads();
     }
+    // every sample belongs to exactly one work item, i.e. to one thread: no race on pc above
+    float2* part = p.part + (((size_t)s * p.C + c) * p.G + g) * (size_t)p.ns_max;
+    for (int j = tid; j < ns; j += THREADS) part[j] = pc[j];
+}
 
-    // ---------------- pass B: corr = A^H c, epilogue ------------------------------------------------------
+// ---------------- solve on the samples ----------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) stream_solve_kernel(K1Params p) {
+    const int c = blockIdx.x, s = blockIdx.y;
+    const int f0 = p.frame_ptr[c];
+    const int ns = p.frame_ptr[c + 1] - f0;
+    const float inv_n = 1.0f / (float)NF;  // unitary scaling 1/sqrt(N*M), once per transform direction
+    const float2* part = p.part + ((size_t)s * p.C + c) * p.G * (size_t)p.ns_max;
+    for (int j = threadIdx.x; j < ns; j += blockDim.x) {
+        float sx = 0.f, sy = 0.f;
+        for (int g = 0; g < p.G; ++g) {  // fixed order: deterministic
+            const float2 t = part[(size_t)g * p.ns_max + j];
+            sx += t.x;
+            sy += t.y;
+        }
+        sx *= inv_n;
+        sy *= inv_n;
+        const size_t yi = (size_t)s * p.nmeas + f0 + j;
+        if (MODE == K1_FORWARD) {
+            p.y_out[yi] = make_float2(sx, sy);
+        } else {
+            const float2 y = p.y[yi];
+            const float gsc = p.inv_1p_rho * inv_n;  // (y - A z)/(1 + rho), pre-scaled for the inverse transform
+            p.cbuf[((size_t)s * p.C + c) * p.ns_max + j] = make_float2((y.x - sx) * gsc, (y.y - sy) * gsc);
+        }
+    }
+}
+
+// ---------------- adjoint: corr = A^H c, epilogue --------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 4) stream_adj_kernel(K1Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* ws = reinterpret_cast<float2*>(smem_raw);                  // [MC][CS]
+    float2* tw2 = ws + MC * CS;                                        // [16][16]
+    float2* tw448 = tw2 + 256;                                         // [448]
+    float2* pc = tw448 + 2 * NF;                                       // [ns_max] c
+    float2* ovf = pc + p.ns_max;                                       // [n_ovf][OVF_STRIDE] overflow partials
+    uint32_t* s_ent = reinterpret_cast<uint32_t*>(ovf + (size_t)p.n_ovf * OVF_STRIDE);  // [ns_max]
+    __shared__ float red_min[THREADS / 32], red_max[THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
+    const int f0 = p.frame_ptr[c];
+    const int ns = p.frame_ptr[c + 1] - f0;
+    const size_t img = ((size_t)s * p.C + c) * (size_t)(NF * NF);
+
+    for (int i = tid; i < 256; i += THREADS) tw2[i] = p.tw2[i];
+    for (int i = tid; i < 2 * NF; i += THREADS) tw448[i] = p.tw448[i];
+    for (int i = tid; i < ns; i += THREADS) {
+        s_ent[i] = p.ent[f0 + i];
+        if (MODE == K1_ADJOINT) {
+            const float2 y = p.y[(size_t)s * p.nmeas + f0 + i];
+            pc[i] = make_float2(y.x * (1.0f / (float)NF), y.y * (1.0f / (float)NF));
+        } else {
+            pc[i] = p.cbuf[((size_t)s * p.C + c) * p.ns_max + i];
+        }
+    }
+    const uint32_t itA = p.itA[(size_t)c * NF + tid], itB = p.itB[(size_t)c * NF + tid];
+    const int l16 = tid & 15;
+    const int col = tid >> 4;
+    float2* colp = ws + col * CS;
+    __syncthreads();
+
     float lmin = INFINITY, lmax = -INFINITY;
+    const int slab0 = g * p.slabs_per_cta;
 #pragma unroll 1
-    for (int slab = 0; slab < SLABS; ++slab) {
-        const int m0 = slab * MC;
-        p4_row<HC>(ws + half * HC * CS, k1row, my_items, my_cnt, tw, m0 + half * HC, pc);
+    for (int sl = 0; sl < p.slabs_per_cta; ++sl) {
+        const int m0 = (slab0 + sl) * MC;
+        const size_t gi = img + (size_t)(m0 + col) * NF + l16;
+        // what the correction is added to (v in ADMM mode, z in SOLVE mode) is wanted only after the transform: ask for the
+        // lines now (no register cost), load them in the epilogue
+        if (MODE == K1_ADMM) {
+#pragma unroll
+            for (int d = 0; d < 14; ++d) prefetch_l1(p.v + gi + 16 * d);
+        } else if (MODE == K1_SOLVE) {
+#pragma unroll
+            for (int d = 0; d < 14; ++d) {
+                prefetch_l1(p.in_re + gi + 16 * d);
+                if (p.in_im) prefetch_l1(p.in_im + gi + 16 * d);
+            }
+        }
+        {
+            const Item it = decode_item(itA, itB);
+            if (it.k1 != 255) {
+                float2 SP[NP_STREAM], SM[NP_STREAM];
+                p4_item_partial(SP, SM, s_ent + it.start, it.cnt, tw448, m0, pc);
+                if (it.slot == 0) p4_item_store(ws, it.k1, SP, SM);
+                else p4_item_spill(ovf + (size_t)(it.slot - 1) * OVF_STRIDE, SP, SM);
+            }
+            if (it.zrow != 255) p4_zero_row(ws, it.zrow);
+        }
+        if (p.n_ovf) {
+            __syncthreads();
+            const Item it = decode_item(itA, itB);
+            if (it.k1 != 255 && it.slot == 0 && it.novf) p4_row_add_overflow(ws, it.k1, ovf + (size_t)it.ovf0 * OVF_STRIDE, it.novf);
+        }
         __syncthreads();
         {
-            const size_t g = img + (size_t)(m0 + col) * NF + l16;
-            // what the correction is added to (v in ADMM mode, z in SOLVE mode) is wanted only after the transform: ask for
-            // the lines now (no register cost), load them in the epilogue
-            if (MODE == K1_ADMM) {
-#pragma unroll
-                for (int d = 0; d < 14; ++d) prefetch_l1(p.v + g + 16 * d);
-            } else if (MODE == K1_SOLVE) {
-#pragma unroll
-                for (int d = 0; d < 14; ++d) {
-                    prefetch_l1(p.in_re + g + 16 * d);
-                    if (p.in_im) prefetch_l1(p.in_im + g + 16 * d);
-                }
-            }
-            float2* colp = ws + col * CS;
             float2 a[16];
             if (l16 < 14) inv_s1_load(colp, l16, tw2, a);
             __syncwarp();
@@ -159,20 +225,20 @@ __global__ void __launch_bounds__(THREADS, 2) xupdate_stream_kernel(K1Params p) 
             float br[14], bi[14];
             if (MODE == K1_ADMM) {
 #pragma unroll
-                for (int d = 0; d < 14; ++d) br[d] = __ldg(p.v + g + 16 * d);
+                for (int d = 0; d < 14; ++d) br[d] = __ldg(p.v + gi + 16 * d);
             } else if (MODE == K1_SOLVE) {
 #pragma unroll
                 for (int d = 0; d < 14; ++d) {
-                    br[d] = __ldg(p.in_re + g + 16 * d);
-                    bi[d] = p.in_im ? __ldg(p.in_im + g + 16 * d) : 0.f;
+                    br[d] = __ldg(p.in_re + gi + 16 * d);
+                    bi[d] = p.in_im ? __ldg(p.in_im + gi + 16 * d) : 0.f;
                 }
             }
             if (MODE == K1_ADMM && p.x_re) {  // last iteration: x = z + corr = 2 v - w + corr; w' may overwrite w in place, so x goes first
 #pragma unroll
                 for (int d = 0; d < 14; ++d) {
-                    const float wr = __ldcs(p.in_re + g + 16 * d), wi = __ldcs(p.in_im + g + 16 * d);
-                    p.x_re[g + 16 * d] = 2.f * br[d] - wr + a[d].x;
-                    p.x_im[g + 16 * d] = a[d].y - wi;
+                    const float wr = __ldcs(p.in_re + gi + 16 * d), wi = __ldcs(p.in_im + gi + 16 * d);
+                    p.x_re[gi + 16 * d] = 2.f * br[d] - wr + a[d].x;
+                    p.x_im[gi + 16 * d] = a[d].y - wi;
                 }
             }
 #pragma unroll
@@ -188,8 +254,8 @@ __global__ void __launch_bounds__(THREADS, 2) xupdate_stream_kernel(K1Params p) 
                     ore = a[d].x;
                     oim = a[d].y;
                 }
-                p.out_re[g + 16 * d] = ore;
-                p.out_im[g + 16 * d] = oim;
+                p.out_re[gi + 16 * d] = ore;
+                p.out_im[gi + 16 * d] = oim;
                 lmin = fminf(lmin, ore);
                 lmax = fmaxf(lmax, ore);
             }
@@ -218,32 +284,68 @@ __global__ void __launch_bounds__(THREADS, 2) xupdate_stream_kernel(K1Params p) 
     }
 }
 
+size_t fwd_smem(const K1Params& p) { return (size_t)(MC * CS + 256 + 2 * NF + p.ns_max) * sizeof(float2) + (size_t)p.ns_max * 4 + 16; }
+size_t adj_smem(const K1Params& p) {
+    return (size_t)(MC * CS + 256 + 2 * NF + p.ns_max + (size_t)p.n_ovf * OVF_STRIDE) * sizeof(float2) + (size_t)p.ns_max * 4 + 16;
+}
+
 template <int MODE>
-int launch_mode(qmri_ctx* ctx, const K1Params& p, int S, size_t smem) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        QCUDA(cudaFuncSetAttribute(xupdate_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+int launch_mode(qmri_ctx* ctx, const K1Params& p, int S) {
+    static size_t conf_f = 0, conf_a = 0;
+    const size_t sf = fwd_smem(p), sa = adj_smem(p);
+    if (sf > conf_f) {
+        QCUDA(cudaFuncSetAttribute(stream_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
+        conf_f = sf;
     }
-    xupdate_stream_kernel<MODE><<<dim3(p.C, S), THREADS, smem, ctx->stream>>>(p);
-    QLAUNCH_CHECK(ctx);
+    if (sa > conf_a) {
+        QCUDA(cudaFuncSetAttribute(stream_adj_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa));
+        conf_a = sa;
+    }
+    if (MODE != K1_ADJOINT) {
+        stream_fwd_kernel<MODE><<<dim3(p.G, p.C, S), THREADS, sf, ctx->stream>>>(p);
+        QLAUNCH_CHECK(ctx);
+        stream_solve_kernel<MODE><<<dim3(p.C, S), 256, 0, ctx->stream>>>(p);
+        QLAUNCH_CHECK(ctx);
+    }
+    if (MODE != K1_FORWARD) {
+        stream_adj_kernel<MODE><<<dim3(p.G, p.C, S), THREADS, sa, ctx->stream>>>(p);
+        QLAUNCH_CHECK(ctx);
+    }
     return QMRI_OK;
 }
 
 }  // namespace
 
-bool k1_stream_supported(int max_row, int ns_max) { return max_row <= RMAX_STREAM && ns_max <= 4096; }
+// Number of slab groups per image: the split that leaves the shortest last wave (four CTAs per SM), smallest first.
+int k1_stream_groups(int S, int C, int sm_count) {
+    const double slots = 4.0 * sm_count;
+    int best = 2;
+    double best_loss = 1e30;
+    for (int G = 2; G <= SLABS; G *= 2) {
+        const double waves = (double)S * C * G / slots;
+        const double loss = ceil(waves) / waves;
+        if (loss < best_loss - 0.02) {
+            best_loss = loss;
+            best = G;
+        }
+    }
+    return best;
+}
+size_t k1_stream_part_elems(int S, int C, int G, int ns_max) { return (size_t)S * C * G * ns_max; }
+size_t k1_stream_cbuf_elems(int S, int C, int ns_max) { return (size_t)S * C * ns_max; }
 
 int k1_stream_launch(qmri_ctx* ctx, const K1Params& p_in, int S, int ns_max) {
     if (S <= 0) return QMRI_OK;
     if (S > 65535) return qmri_fail(QMRI_EINVAL, "x-update: at most 65535 slices per launch (got %d)", S);
     K1Params p = p_in;
     p.ns_max = ns_max;
-    const size_t smem = (size_t)(MC * CS + NF + 256 + 2 * ns_max) * sizeof(float2) + (size_t)ns_max * 4 + (size_t)(NF + 1) * 2 + 16;
+    if (p.G < 1 || SLABS % p.G || !p.part || !p.cbuf) return qmri_fail(QMRI_EINVAL, "x-update (streaming kernel): bad slab grouping / scratch");
+    p.slabs_per_cta = SLABS / p.G;
+    if (adj_smem(p) > 56 * 1024) return qmri_fail(QMRI_EUNSUPPORTED, "x-update (streaming kernel): %zu bytes of shared memory needed", adj_smem(p));
     switch (p.mode) {
-        case K1_ADMM: return launch_mode<K1_ADMM>(ctx, p, S, smem);
-        case K1_SOLVE: return launch_mode<K1_SOLVE>(ctx, p, S, smem);
-        case K1_FORWARD: return launch_mode<K1_FORWARD>(ctx, p, S, smem);
-        default: return launch_mode<K1_ADJOINT>(ctx, p, S, smem);
+        case K1_ADMM: return launch_mode<K1_ADMM>(ctx, p, S);
+        case K1_SOLVE: return launch_mode<K1_SOLVE>(ctx, p, S);
+        case K1_FORWARD: return launch_mode<K1_FORWARD>(ctx, p, S);
+        default: return launch_mode<K1_ADJOINT>(ctx, p, S);
     }
 }

@@ -488,11 +488,23 @@ def test_stream_kernel_with_builtin_unetres_and_graph(q, stream_op):
     assert rel_l2(x, xo) <= 1e-4
 
 
-def test_stream_kernel_refuses_line_sampled_masks(q, monkeypatch):
+def test_stream_kernel_line_sampled_mask(q, monkeypatch):
+    """EPI rows hold 224 samples each: they are cut into chunks whose partial sums meet in shared-memory overflow slots."""
+    from oracle import sampling
+    from oracle.sampling import FOperator
+    from oracle.xupdate import xupdate_exact
     monkeypatch.setenv("QMRI_K1_KERNEL", "stream")
-    P = q.setup_subsampling_epi(224, 224, 1 / 65, np.eye(10))
-    with pytest.raises(q.QmriError):
-        q.fft_operator(P).forward(np.zeros((224, 224, 10)))
+    V = np.eye(10)
+    P, Po = q.setup_subsampling_epi(224, 224, 1 / 65, V), sampling.setup_subsampling_epi(224, 224, 1 / 65, V)
+    F, Fo = q.fft_operator(P), FOperator(Po)
+    x = smooth_tsmi(41, cplx=True)
+    assert rel_l2(F.forward(x), Fo.forward(x)) <= TOL_XUPDATE
+    rng = np.random.default_rng(4)
+    b = rng.standard_normal(P.nmeas) + 1j * rng.standard_normal(P.nmeas)
+    assert rel_l2(F.adjoint(b), Fo.adjoint(b)) <= TOL_XUPDATE
+    y = Fo.forward(smooth_tsmi(42))
+    v, u = smooth_tsmi(43), 0.1 * smooth_tsmi(44, cplx=True)
+    assert rel_l2(F.xupdate(y, v, u, 0.05), xupdate_exact(Fo, y, v - u, 0.05)) <= TOL_XUPDATE
 
 
 def test_large_batch_takes_streaming_kernel_and_matches_oracle(q, ops):

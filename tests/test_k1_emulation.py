@@ -52,7 +52,7 @@ def test_cxx_mask_constructors_equal_oracle(emu, pat, arg):
         assert np.array_equal(idx, Po.idx) and np.array_equal(fptr, Po.frame_ptr)
 
 
-@pytest.mark.parametrize("pat,arg,mc", [(0, 771.0, 28), (0, 771.0, 56), (1, 1 / 65, 28), (0, 771.0, 0)])  # mc 0 = streaming kernel
+@pytest.mark.parametrize("pat,arg,mc", [(0, 771.0, 28), (0, 771.0, 56), (1, 1 / 65, 28), (0, 771.0, 0), (1, 1 / 65, 0)])  # mc 0 = streaming kernel
 def test_k1_arithmetic_all_modes(emu, pat, arg, mc):
     C = 3
     Po = (sampling.setup_subsampling_spiralgrided(224, 224, 771, np.eye(C)) if pat == 0
