@@ -219,16 +219,15 @@ static void emulate_stream(int mode, int C, int S, const optab::K1Tables& t, con
                 std::vector<float2> ovf((size_t)std::max(t.n_ovf, 1) * OVF_STRIDE, float2{0, 0});
                 for (int sl = 0; sl < SPC; ++sl) {
                     const int m0 = (g * SPC + sl) * MC;
+                    for (auto& e : ws) e = float2{NAN, NAN};  // rows without samples are never written: they must never be read either
                     for (int tid = 0; tid < THREADS; ++tid) {
                         const int k1row = (int)(itA[tid] & 0xffu), cnt = (int)((itA[tid] >> 8) & 0xffu), slot = (int)(itB[tid] & 0xffu);
-                        const int zrow = (int)(itB[tid] >> 24);
                         if (k1row != 255) {
                             float2 SP[NP_STREAM], SM[NP_STREAM];
                             p4_item_partial(SP, SM, ent + (itA[tid] >> 16), cnt, tw448, m0, cvec.data());
                             if (slot == 0) p4_item_store(ws.data(), k1row, SP, SM);
                             else p4_item_spill(ovf.data() + (size_t)(slot - 1) * OVF_STRIDE, SP, SM);
                         }
-                        if (zrow != 255) p4_zero_row(ws.data(), zrow);
                     }
                     for (int tid = 0; tid < THREADS; ++tid) {
                         const int k1row = (int)(itA[tid] & 0xffu), slot = (int)(itB[tid] & 0xffu);
@@ -236,7 +235,7 @@ static void emulate_stream(int mode, int C, int S, const optab::K1Tables& t, con
                         if (k1row != 255 && slot == 0 && novf) p4_row_add_overflow(ws.data(), k1row, ovf.data() + (size_t)ovf0 * OVF_STRIDE, novf);
                     }
                     for (int tid = 0; tid < THREADS; ++tid)
-                        if ((tid & 15) < 14) inv_s1_load(ws.data() + (tid >> 4) * CS, tid & 15, tw2, A(tid));
+                        if ((tid & 15) < 14) inv_s1_load(ws.data() + (tid >> 4) * CS, tid & 15, tw2, t.rowmask[(size_t)c * 16 + (tid & 15)], A(tid));
                     for (int tid = 0; tid < THREADS; ++tid)
                         if ((tid & 15) < 14) inv_s1_store(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
                     for (int tid = 0; tid < THREADS; ++tid) {

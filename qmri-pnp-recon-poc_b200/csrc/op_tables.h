@@ -82,6 +82,7 @@ struct K1Tables {
     std::vector<uint32_t> itA;        // [C][N] k1 | cnt << 8 | start << 16   (k1 == 255: thread has no item)
     std::vector<uint32_t> itB;        // [C][N] slot | novf << 8 | ovf0 << 16 | zrow << 24   (zrow == 255: none)
     std::vector<uint32_t> ent;        // [nmeas] j | k2 << 16, frame-major, grouped by item
+    std::vector<uint16_t> rowmask;    // [C][16] bit a of entry b: row 14 a + b holds samples (inverse FFT stage 1 skips empty rows)
     int n_ovf = 0;                    // largest number of overflow partials in one frame
     int max_row = 0;                  // largest number of samples in one row of one frame
     std::vector<float> tw2;           // [16][16][2]  e^{-2 pi i (i j) / N}
@@ -105,11 +106,12 @@ constexpr int STREAM_OVF_MAX = 96;   // == k1::OVF_MAX_STREAM
 // without samples are zero-filled by a thread that is handed the row as a side duty.  Lane placement: thread 16 h + l takes
 // an item of residue class l (k1 = l mod 16) whenever one is left, heaviest first, so the 16 lanes of a half-warp address 16
 // different bank pairs in the [column][k1] workspace and the items of a warp carry similar sample counts.
-static inline void build_stream_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t) {
+static inline void build_stream_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t, int q_min = 1) {
     t.stream_ok = (N % 16 == 0) && N <= 254;
     t.itA.assign((size_t)t.C * N, 255u);
     t.itB.assign((size_t)t.C * N, 255u << 24);
     t.ent.assign(std::max(t.nmeas, 1), 0);
+    t.rowmask.assign((size_t)t.C * 16, 0);
     t.n_ovf = 0;
     t.max_row = 0;
     if (!t.stream_ok) return;
@@ -118,9 +120,12 @@ static inline void build_stream_tables(int N, const std::vector<std::vector<int3
         const auto& f = frames[c];
         std::vector<std::vector<uint32_t>> rows(N);
         for (int j = 0; j < (int)f.size(); ++j) rows[f[j] % N].push_back((uint32_t)j | ((uint32_t)(f[j] / N) << 16));
-        for (int k = 0; k < N; ++k) t.max_row = std::max(t.max_row, (int)rows[k].size());
+        for (int k = 0; k < N; ++k) {
+            t.max_row = std::max(t.max_row, (int)rows[k].size());
+            if (!rows[k].empty() && N == 224) t.rowmask[(size_t)c * 16 + k % 14] |= (uint16_t)(1u << (k / 14));
+        }
         int Q = 0;
-        for (int q = 1; q <= STREAM_QMAX && !Q; ++q) {
+        for (int q = std::max(1, q_min); q <= STREAM_QMAX && !Q; ++q) {
             int items = 0, ovf = 0;
             for (int k = 0; k < N; ++k) {
                 int n = ((int)rows[k].size() + q - 1) / q;
@@ -162,13 +167,7 @@ static inline void build_stream_tables(int N, const std::vector<std::vector<int3
         std::stable_sort(left.begin(), left.end(), [&](int a, int b2) { return items[a].cnt > items[b2].cnt; });
         for (int tid = 0, q = 0; tid < N && q < (int)left.size(); ++tid)
             if (place[tid] < 0) place[tid] = left[q++];
-        // zero-fill duties: rows without samples, handed out from the last thread backwards (the lightest items)
-        std::vector<int> zrow(N, 255);
-        {
-            int tid = N - 1;
-            for (int k = 0; k < N; ++k)
-                if (rows[k].empty()) zrow[tid--] = k;
-        }
+        std::vector<int> zrow(N, 255);  // (rows without samples are skipped by the inverse FFT through `rowmask`: no zero fill)
         size_t pos = 0;
         for (int tid = 0; tid < N; ++tid) {
             uint32_t A = 255u, B = (uint32_t)zrow[tid] << 24;
@@ -186,7 +185,7 @@ static inline void build_stream_tables(int N, const std::vector<std::vector<int3
     }
 }
 
-static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t) {
+static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t, int stream_q_min = 1) {
     t.C = (int)frames.size();
     t.frame_ptr.assign(t.C + 1, 0);
     for (int c = 0; c < t.C; ++c) t.frame_ptr[c + 1] = t.frame_ptr[c] + (int)frames[c].size();
@@ -231,7 +230,7 @@ static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>
     for (int c = 0; c < t.C; ++c)
         for (int ph = 0; ph < K1_PHASES; ++ph)
             std::copy(lists[c][ph].begin(), lists[c][ph].end(), t.p4tab.begin() + ((size_t)c * K1_PHASES + ph) * t.p4_len);
-    build_stream_tables(N, frames, t);
+    build_stream_tables(N, frames, t, stream_q_min);
     t.tw.resize(2 * N);
     const double PI = 3.14159265358979323846;
     t.tw448.resize(4 * N);

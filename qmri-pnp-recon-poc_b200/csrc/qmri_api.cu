@@ -240,6 +240,7 @@ struct qmri_op {
     uint32_t* d_itA = nullptr;
     uint32_t* d_itB = nullptr;
     uint32_t* d_ent = nullptr;
+    uint16_t* d_rowmask = nullptr;
     int k1_kernel = 0;  // 0 = choose by batch size, 1 = cluster kernel, 2 = streaming kernel (QMRI_K1_KERNEL=cluster|stream)
     // scratch for the host entry points
     DevBuf stage, a_re, a_im, b_re, b_im, c_re, c_im, ybuf, mm_ord, mm_f;
@@ -276,7 +277,8 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     env = getenv("QMRI_K1_KERNEL");
     if (env && !strcmp(env, "cluster")) op->k1_kernel = 1;
     if (env && !strcmp(env, "stream")) op->k1_kernel = 2;
-    optab::build_k1_tables(N, frames, op->t);
+    env = getenv("QMRI_K1_QMIN");  // tuning knob: smallest chunk size tried for the streaming kernel's work items
+    optab::build_k1_tables(N, frames, op->t, env ? atoi(env) : 8);  // 8: measured best on the spiral masks (fewer overflow partials)
     const optab::K1Tables& t = op->t;
     size_t nm = std::max(1, t.nmeas);
     int r = 0;
@@ -289,6 +291,7 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     r |= dev_alloc(&op->d_itA, t.itA.size());
     r |= dev_alloc(&op->d_itB, t.itB.size());
     r |= dev_alloc(&op->d_ent, t.ent.size());
+    r |= dev_alloc(&op->d_rowmask, t.rowmask.size());
     if (r) {
         qmri_op_destroy(op);
         return QMRI_ENOMEM;
@@ -301,6 +304,7 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     cudaMemcpy(op->d_itA, t.itA.data(), sizeof(uint32_t) * t.itA.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_itB, t.itB.data(), sizeof(uint32_t) * t.itB.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_ent, t.ent.data(), sizeof(uint32_t) * t.ent.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_rowmask, t.rowmask.data(), sizeof(uint16_t) * t.rowmask.size(), cudaMemcpyHostToDevice);
     cudaError_t e = cudaMemcpy(op->d_p4tab, t.p4tab.data(), sizeof(uint32_t) * t.p4tab.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         qmri_op_destroy(op);
@@ -339,7 +343,7 @@ extern "C" int qmri_op_destroy(qmri_op* op) {
     cudaStreamSynchronize(op->ctx->stream);
     cudaFree(op->d_tw); cudaFree(op->d_frame_ptr); cudaFree(op->d_samp);
     cudaFree(op->d_p4tab);
-    cudaFree(op->d_tw2); cudaFree(op->d_tw448); cudaFree(op->d_itA); cudaFree(op->d_itB); cudaFree(op->d_ent);
+    cudaFree(op->d_tw2); cudaFree(op->d_tw448); cudaFree(op->d_itA); cudaFree(op->d_itB); cudaFree(op->d_ent); cudaFree(op->d_rowmask);
     op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
     op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
     op->k1_part.release(); op->k1_cbuf.release();
@@ -355,14 +359,19 @@ extern "C" int qmri_op_indices(const qmri_op* op, int32_t* idx, int64_t* frame_p
     return QMRI_OK;
 }
 
-// Kernel choice for one x-update launch: the streaming kernel (one CTA per slice-channel, xupdate_stream.cu) once the batch
-// fills the machine, the cluster kernel (eight CTAs per slice-channel, xupdate_kernel.cu) for small batches and for masks
-// with densely sampled k-space rows (EPI lines).  QMRI_K1_KERNEL=cluster|stream forces one (tests, profiling).
-static int k1_dispatch(qmri_op* op, const K1Params& p_in, int S) {
+// Kernel choice for one x-update launch: the streaming kernels (xupdate_stream.cu: forward / solve / adjoint, up to 16 CTAs
+// per slice-channel image) from about two slices on, the single cluster kernel (xupdate_kernel.cu: the image stays in the
+// shared memory of eight CTAs) below that - measured on B200: 23.8 vs 27.0 us at one slice, 16.2 vs 15.5 us at two, 9.1 vs
+// 7.4 us at eight, 6.97 vs 4.37 us per slice at 120.  QMRI_K1_KERNEL=cluster|stream forces one (tests, profiling).
+// part / cbuf: scratch of the streaming kernels.  The host entry points use the operator's; an ADMM session brings its own,
+// sized once for its batch, because its CUDA graph keeps the addresses.
+static int k1_dispatch(qmri_op* op, const K1Params& p_in, int S, DevBuf* part = nullptr, DevBuf* cbuf = nullptr) {
     K1Params p = p_in;
+    if (!part) part = &op->k1_part;
+    if (!cbuf) cbuf = &op->k1_cbuf;
     qmri_ctx* ctx = op->ctx;
     const bool can_stream = op->t.stream_ok;
-    bool stream = can_stream && (long long)S * op->C >= K1_STREAM_MIN_CTAS_PER_SM * (long long)ctx->sm_count;
+    bool stream = can_stream && (long long)S * op->C * K1_STREAM_MIN_IMAGES_DIV >= (long long)ctx->sm_count;
     if (op->k1_kernel == 1) stream = false;
     if (op->k1_kernel == 2) {
         if (!can_stream)
@@ -371,11 +380,11 @@ static int k1_dispatch(qmri_op* op, const K1Params& p_in, int S) {
     }
     if (stream) {
         p.G = k1_stream_groups(S, op->C, ctx->sm_count);
-        // (re)allocation happens on the first launch of a batch size, i.e. before any CUDA-graph capture of the loop
-        QCHECK(op->k1_part.ensure(k1_stream_part_elems(S, op->C, p.G, op->t.ns_max) * sizeof(float2)));
-        QCHECK(op->k1_cbuf.ensure(k1_stream_cbuf_elems(S, op->C, op->t.ns_max) * sizeof(float2)));
-        p.part = op->k1_part.as<float2>();
-        p.cbuf = op->k1_cbuf.as<float2>();
+        // allocation happens on the first launch of a batch size, i.e. before any CUDA-graph capture of the loop
+        QCHECK(part->ensure(k1_stream_part_elems(S, op->C, p.G, op->t.ns_max) * sizeof(float2)));
+        QCHECK(cbuf->ensure(k1_stream_cbuf_elems(S, op->C, op->t.ns_max) * sizeof(float2)));
+        p.part = part->as<float2>();
+        p.cbuf = cbuf->as<float2>();
         return k1_stream_launch(ctx, p, S, op->t.ns_max);
     }
     return k1_launch(ctx, p, S, op->t.ns_max, op->k1_mc);
@@ -392,6 +401,7 @@ static void k1_fill_tables(const qmri_op* op, K1Params& p) {
     p.itA = op->d_itA;
     p.itB = op->d_itB;
     p.ent = op->d_ent;
+    p.rowmask = op->d_rowmask;
     p.n_ovf = op->t.n_ovf;
     p.C = op->C;
     p.nmeas = op->t.nmeas;
@@ -613,6 +623,7 @@ struct qmri_admm {
     int S = 0;
     qmri_admm_params prm;
     DevBuf y, x0_re, x0_im, w_re, w_im, v, x_re, x_im, mm_ord, mm_f, noise, cb_in, cb_out;
+    DevBuf k1_part, k1_cbuf;  // streaming x-update scratch (addresses are baked into the session's CUDA graph)
     float *h_in = nullptr, *h_out = nullptr;  // pinned, host-callback path
     bool uploaded = false;
     // one steady-state ADMM iteration (x-update, min/max, 64-conv denoiser = ~130 launches) captured as a CUDA graph:
@@ -688,7 +699,7 @@ extern "C" int qmri_admm_destroy(qmri_admm* st) {
     cudaStreamSynchronize(st->op->ctx->stream);
     st->y.release(); st->x0_re.release(); st->x0_im.release(); st->w_re.release(); st->w_im.release();
     st->v.release(); st->x_re.release(); st->x_im.release(); st->mm_ord.release(); st->mm_f.release();
-    st->noise.release(); st->cb_in.release(); st->cb_out.release();
+    st->noise.release(); st->cb_in.release(); st->cb_out.release(); st->k1_part.release(); st->k1_cbuf.release();
     if (st->h_in) cudaFreeHost(st->h_in);
     if (st->h_out) cudaFreeHost(st->h_out);
     if (st->graph) cudaGraphExecDestroy(st->graph);
@@ -731,7 +742,7 @@ static int admm_k1(qmri_admm* st, bool write_x) {
     p.y = st->y.as<float2>();
     p.minmax = st->mm_ord.as<int>();
     p.inv_1p_rho = (float)(1.0 / (1.0 + st->prm.gamma));
-    return k1_dispatch(op, p, st->S);
+    return k1_dispatch(op, p, st->S, &st->k1_part, &st->k1_cbuf);
 }
 
 static int admm_denoise(qmri_admm* st) {

@@ -33,6 +33,7 @@ struct K1Params {
     const uint32_t* itA;     // [C][224] work item of thread tid: k1 | cnt << 8 | start << 16
     const uint32_t* itB;     // [C][224] slot | novf << 8 | ovf0 << 16 | zrow << 24
     const uint32_t* ent;     // [nmeas] j | k2 << 16, frame-major, grouped by item
+    const uint16_t* rowmask; // [C][16] non-empty rows, by inverse-FFT lane
     int n_ovf;               // overflow partials per frame (sizes the shared-memory slots)
     float2* part;            // scratch [S][C][G][ns_max] partial sample sums of the forward kernel
     float2* cbuf;            // scratch [S][C][ns_max]    c = (y - A z) / (1 + rho)
@@ -46,7 +47,7 @@ struct K1Params {
 };
 
 int k1_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max, int mc);
-constexpr int K1_STREAM_MIN_CTAS_PER_SM = 2;  // use the streaming kernel from S * C >= 2 * SM count on
+constexpr int K1_STREAM_MIN_IMAGES_DIV = 8;  // streaming kernels from S * C >= SM count / 8 images on (two 10-channel slices on B200)
 // streaming variant: one CTA per (slice, channel); needs K1Tables::stream_ok
 int k1_stream_groups(int S, int C, int sm_count);
 size_t k1_stream_part_elems(int S, int C, int G, int ns_max);

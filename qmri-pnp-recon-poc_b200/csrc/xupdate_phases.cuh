@@ -227,6 +227,18 @@ QHD void sparse_idft_flat(float2* col, const float2* c, const float2* twp, const
 constexpr int QMAX_STREAM = 24;      // most samples one work item may carry
 constexpr int OVF_MAX_STREAM = 96;   // most overflow partials (row chunks beyond the first) per frame
 
+// A shared-memory load the compiler keeps in program order (device code): 15 twiddles fetched ahead of their use on top of
+// the 16 complex values of the transform do not fit the 72-register budget of four CTAs per SM.
+QHD float2 ld_ordered(const float2* p) {
+#if defined(__CUDA_ARCH__)
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+}
+
 // forward stage 1 on register inputs: a[n1] = x[16 n1 + n2]
 QHD void fwd_s1_regs(float2 (&a)[16], int n2, const float2* tw2) {
     dft14(a);
@@ -237,12 +249,13 @@ QHD void fwd_s1_regs(float2 (&a)[16], int n2, const float2* tw2) {
 // inverse transform of one column via the swap identity  ifft(U) = swap(fft(swap(U))) (unnormalised):
 // input index k = 14 a + b, output index n = c + 16 d
 //   X[c + 16 d] = sum_b w14^{b d} [ w224^{b c} sum_a U[14 a + b] w16^{a c} ]
-QHD void inv_s1_load(const float2* col, int b, const float2* tw2, float2 (&x)[16]) {
+// mask: bit a set = row 14 a + b holds samples; the other rows of the sparse k-space array are zero and are not read
+QHD void inv_s1_load(const float2* col, int b, const float2* tw2, uint32_t mask, float2 (&x)[16]) {
 #pragma unroll
-    for (int a = 0; a < 16; ++a) x[a] = cswap(col[14 * a + b]);
+    for (int a = 0; a < 16; ++a) x[a] = ((mask >> a) & 1u) ? cswap(col[14 * a + b]) : make_float2(0.f, 0.f);
     dft16(x);
 #pragma unroll
-    for (int c = 1; c < 16; ++c) x[c] = cmul(x[c], tw2[16 * c + b]);
+    for (int c = 1; c < 16; ++c) x[c] = cmul(x[c], ld_ordered(tw2 + 16 * c + b));
 }
 QHD void inv_s1_store(float2* col, int b, const float2 (&x)[16]) {
 #pragma unroll
@@ -281,7 +294,7 @@ QHD void p3_item(const float2* ws, int k1, const uint32_t* ent, int cnt, const f
         const uint32_t en = ent[q];
         const int k2 = (int)(en >> 16), j = (int)(en & 0xffffu);
         float2 r = tw448[k2];          // r_{1/2}
-        const float2 st = tw448[2 * k2];  // e^{-i phi}
+        const float2 st = cmul(r, r);     // e^{-i phi}
         const float2 tc = tw448[(k2 * (2 * m0 + 13)) % (2 * NF)];
         float ax = 0.f, ay = 0.f;
 #pragma unroll
@@ -311,7 +324,7 @@ QHD void p4_item_partial(float2 (&SP)[NP_STREAM], float2 (&SM)[NP_STREAM], const
         const uint32_t en = ent[q];
         const int k2 = (int)(en >> 16), j = (int)(en & 0xffffu);
         float2 r = tw448[k2];
-        const float2 st = tw448[2 * k2];
+        const float2 st = cmul(r, r);
         const float2 tc = tw448[(k2 * (2 * m0 + 13)) % (2 * NF)];
         const float2 u = cmul(pc[j], make_float2(tc.x, -tc.y));
 #pragma unroll

@@ -35,7 +35,11 @@ constexpr int MC = HC_STREAM;         // 14 columns per slab
 constexpr int THREADS = 16 * MC;      // 224: 14 column FFTs x 16 lanes; in the sparse passes one thread per work item
 constexpr int SLABS = NF / MC;        // 16 slabs per image
 
-__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ size_t late_offset(size_t off, float after) {
+    size_t r;
+    asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(off), "f"(after));
+    return r;
+}
 
 struct Item {
     int k1, cnt, start, slot, novf, ovf0, zrow;
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(THREADS, 4) stream_adj_kernel(K1Params p) {
     }
     const uint32_t itA = p.itA[(size_t)c * NF + tid], itB = p.itB[(size_t)c * NF + tid];
     const int l16 = tid & 15;
+    const uint32_t rmask = p.rowmask[c * 16 + l16];
     const int col = tid >> 4;
     float2* colp = ws + col * CS;
     __syncthreads();
@@ -187,18 +192,6 @@ __global__ void __launch_bounds__(THREADS, 4) stream_adj_kernel(K1Params p) {
     for (int sl = 0; sl < p.slabs_per_cta; ++sl) {
         const int m0 = (slab0 + sl) * MC;
         const size_t gi = img + (size_t)(m0 + col) * NF + l16;
-        // what the correction is added to (v in ADMM mode, z in SOLVE mode) is wanted only after the transform: ask for the
-        // lines now (no register cost), load them in the epilogue
-        if (MODE == K1_ADMM) {
-#pragma unroll
-            for (int d = 0; d < 14; ++d) prefetch_l1(p.v + gi + 16 * d);
-        } else if (MODE == K1_SOLVE) {
-#pragma unroll
-            for (int d = 0; d < 14; ++d) {
-                prefetch_l1(p.in_re + gi + 16 * d);
-                if (p.in_im) prefetch_l1(p.in_im + gi + 16 * d);
-            }
-        }
         {
             const Item it = decode_item(itA, itB);
             if (it.k1 != 255) {
@@ -207,7 +200,6 @@ __global__ void __launch_bounds__(THREADS, 4) stream_adj_kernel(K1Params p) {
                 if (it.slot == 0) p4_item_store(ws, it.k1, SP, SM);
                 else p4_item_spill(ovf + (size_t)(it.slot - 1) * OVF_STRIDE, SP, SM);
             }
-            if (it.zrow != 255) p4_zero_row(ws, it.zrow);
         }
         if (p.n_ovf) {
             __syncthreads();
@@ -217,20 +209,23 @@ __global__ void __launch_bounds__(THREADS, 4) stream_adj_kernel(K1Params p) {
         __syncthreads();
         {
             float2 a[16];
-            if (l16 < 14) inv_s1_load(colp, l16, tw2, a);
+            if (l16 < 14) inv_s1_load(colp, l16, tw2, rmask, a);
             __syncwarp();
             if (l16 < 14) inv_s1_store(colp, l16, a);
             __syncwarp();
             inv_s2_regs(colp, l16, a);
+            // What the correction is added to (v in ADMM mode, z in SOLVE mode).  The offset is made to depend on the transform's
+            // last output so that the 14 - 28 loads are not hoisted above it: held across the transform they spill.
+            const size_t gl = late_offset(gi, a[13].y);
             float br[14], bi[14];
             if (MODE == K1_ADMM) {
 #pragma unroll
-                for (int d = 0; d < 14; ++d) br[d] = __ldg(p.v + gi + 16 * d);
+                for (int d = 0; d < 14; ++d) br[d] = __ldg(p.v + gl + 16 * d);
             } else if (MODE == K1_SOLVE) {
 #pragma unroll
                 for (int d = 0; d < 14; ++d) {
-                    br[d] = __ldg(p.in_re + gi + 16 * d);
-                    bi[d] = p.in_im ? __ldg(p.in_im + gi + 16 * d) : 0.f;
+                    br[d] = __ldg(p.in_re + gl + 16 * d);
+                    bi[d] = p.in_im ? __ldg(p.in_im + gl + 16 * d) : 0.f;
                 }
             }
             if (MODE == K1_ADMM && p.x_re) {  // last iteration: x = z + corr = 2 v - w + corr; w' may overwrite w in place, so x goes first
@@ -316,20 +311,15 @@ int launch_mode(qmri_ctx* ctx, const K1Params& p, int S) {
 
 }  // namespace
 
-// Number of slab groups per image: the split that leaves the shortest last wave (four CTAs per SM), smallest first.
+// Number of slab groups (CTAs) per image: the coarsest split whose last wave wastes <= 6 % (four CTAs per SM resident), else
+// the finest.  Coarser groups stage the operator tables less often; finer groups shorten the tail.
 int k1_stream_groups(int S, int C, int sm_count) {
     const double slots = 4.0 * sm_count;
-    int best = 2;
-    double best_loss = 1e30;
-    for (int G = 2; G <= SLABS; G *= 2) {
+    for (int G = 4; G <= SLABS; G *= 2) {
         const double waves = (double)S * C * G / slots;
-        const double loss = ceil(waves) / waves;
-        if (loss < best_loss - 0.02) {
-            best_loss = loss;
-            best = G;
-        }
+        if (ceil(waves) / waves <= 1.06) return G;
     }
-    return best;
+    return SLABS;
 }
 size_t k1_stream_part_elems(int S, int C, int G, int ns_max) { return (size_t)S * C * G * ns_max; }
 size_t k1_stream_cbuf_elems(int S, int C, int ns_max) { return (size_t)S * C * ns_max; }

@@ -460,9 +460,11 @@ def test_stream_kernel_operator_and_xupdate(q, stream_op):
     assert abs(mm[1] - wo.real.max()) <= 1e-5 * abs(wo.real).max()
 
 
-def test_stream_kernel_admm_loop_and_agreement_with_cluster_kernel(q, ops, stream_op):
+def test_stream_kernel_admm_loop_and_agreement_with_cluster_kernel(q, stream_op, monkeypatch):
     from oracle.admm import pnp_admm
     P, Po = stream_op
+    monkeypatch.setenv("QMRI_K1_KERNEL", "cluster")
+    Pc = q.setup_subsampling_spiralgrided(224, 224, 771, np.eye(10))
     Fo, Xgt, Y, X0 = make_problem(Po, 36, S=2)
     Y[:, 1] *= 2.0
     X0 = Fo.adjoint(Y)
@@ -471,7 +473,7 @@ def test_stream_kernel_admm_loop_and_agreement_with_cluster_kernel(q, ops, strea
     for s in range(2):
         xo = pnp_admm(Y[:, s], dict(param, F=Fo, net=box_denoiser, X0=X0[..., s]), solver="exact")
         assert rel_l2(x[..., s], xo) <= TOL_XUPDATE
-    xc = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(ops["spiral"][0]), net=box_denoiser, X0=X0))  # cluster kernel (S*C small)
+    xc = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(Pc), net=box_denoiser, X0=X0))
     assert rel_l2(x, xc) <= 2e-6
 
 
@@ -507,8 +509,26 @@ def test_stream_kernel_line_sampled_mask(q, monkeypatch):
     assert rel_l2(F.xupdate(y, v, u, 0.05), xupdate_exact(Fo, y, v - u, 0.05)) <= TOL_XUPDATE
 
 
+def test_cluster_kernel_batched(q, monkeypatch):
+    """Batches of two slices or more default to the streaming kernels; the cluster kernel must stay correct for them too."""
+    from oracle import sampling
+    from oracle.sampling import FOperator
+    from oracle.xupdate import xupdate_exact
+    monkeypatch.setenv("QMRI_K1_KERNEL", "cluster")
+    V = np.eye(10)
+    P, Po = q.setup_subsampling_spiralgrided(224, 224, 771, V), sampling.setup_subsampling_spiralgrided(224, 224, 771, V)
+    F, Fo = q.fft_operator(P), FOperator(Po)
+    x = smooth_tsmi(51, S=3, cplx=True)
+    y = F.forward(x)
+    for s in range(3):
+        assert rel_l2(y[:, s], Fo.forward(x[..., s])) <= TOL_XUPDATE
+    yv = Fo.forward(smooth_tsmi(52))
+    v, u = smooth_tsmi(53), 0.1 * smooth_tsmi(54, cplx=True)
+    assert rel_l2(F.xupdate(yv, v, u, 0.05), xupdate_exact(Fo, yv, v - u, 0.05)) <= TOL_XUPDATE
+
+
 def test_large_batch_takes_streaming_kernel_and_matches_oracle(q, ops):
-    """S * C >= 2 * SM count switches to the streaming kernel on its own: 32 slices, spot-check four of them."""
+    """Two slices or more take the streaming kernels on their own: 32 slices (one short last wave), spot-check four of them."""
     from oracle.sampling import FOperator
     from oracle.xupdate import xupdate_exact
     P, Po = ops["spiral"]
