@@ -244,14 +244,22 @@ __global__ void __launch_bounds__(256) resample_gemm_fp32_kernel(ConvParams p) {
 // head: planar [S][Cin][H][W] (+ optional shared noise-map plane as last channel) -> [S][H][W][64]
 // with v_in = (x - min) / range folded into the load (PnP_ADMM.m:121,177-182; no zero-range guard).
 // ---------------------------------------------------------------------------------------
+// Register-blocked: a thread owns 4 consecutive pixels of a row x 16 of the 64 output channels (cb = tid & 3 picks the 16), so the
+// six patch values of a (row, input channel) serve 3 taps x 4 pixels and every weight load feeds 64 FMAs (a thread per pixel
+// issued 5 shared-memory loads per 16 FMAs and staged its patch with one scalar load in flight: 51 us for one slice).
+// CTA = 256 threads = a 32 x 8 pixel tile x 64 channels, 196 tiles per slice; the four cb lanes of a pixel group write the four
+// 32-byte quarters of the same 128-byte NHWC line.
+constexpr int HT_TW = 32, HT_PITCH = 36;   // tile width; patch row pitch in floats (34 used; 36 keeps rows 16-byte aligned)
+constexpr int HEAD_TH = 8, HEAD_ROWS = HEAD_TH + 2;
+constexpr int HEAD_WPITCH = 80;            // weights [9][Cin][4 cb][20]: 20-float blocks put the four cb lanes on different banks
 __global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
     extern __shared__ __align__(16) float hsm[];
     const int Cin = p.Cin;
-    float* patch = hsm;                  // [Cin][18][18]
-    float* wts = hsm + Cin * 324;        // [9][Cin][64]
+    float* patch = hsm;                                  // [Cin][10][36]
+    float* wts = hsm + Cin * HEAD_ROWS * HT_PITCH;       // [9][Cin][80]
     const int tid = threadIdx.x;
-    const int tiles_x = (p.W + 15) / 16;
-    const int ty0 = (blockIdx.x / tiles_x) * 16, tx0 = (blockIdx.x % tiles_x) * 16;
+    const int tiles_x = (p.W + HT_TW - 1) / HT_TW;
+    const int ty0 = (blockIdx.x / tiles_x) * HEAD_TH, tx0 = (blockIdx.x % tiles_x) * HT_TW;
     const int s = blockIdx.z;
     float mn = 0.f, inv = 1.f;
     if (p.minmax) {
@@ -259,45 +267,78 @@ __global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
         inv = 1.0f / (p.minmax[2 * s + 1] - mn);
     }
     const int Cpl = p.noise_map ? Cin - 1 : Cin;  // channels stored in the planar input
-    for (int t = tid; t < Cin * 324; t += 256) {
-        int c = t / 324, r = t % 324;
-        int y = ty0 + r / 18 - 1, x = tx0 + r % 18 - 1;
-        float v = 0.f;
-        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-            if (c < Cpl) v = (__ldg(p.planar_in + (((size_t)s * Cpl + c) * p.H + y) * p.W + x) - mn) * inv;
-            else v = __ldg(p.noise_map + (size_t)y * p.W + x);
-        }
-        patch[t] = v;
-    }
-    for (int t = tid; t < 9 * Cin * 16; t += 256)
-        reinterpret_cast<float4*>(wts)[t] = __ldg(reinterpret_cast<const float4*>(p.w) + t);
-    __syncthreads();
-    const int ty = tid >> 4, tx = tid & 15;
-    const int y = ty0 + ty, x = tx0 + tx;
-    for (int cb = 0; cb < 64; cb += 16) {
-        float acc[16];
+    // patch staging: a warp takes whole rows (34 pixels: lane -> x, lanes 0-1 also the last two), four rows in flight
+    {
+        const int lane = tid & 31, wrp = tid >> 5;
+        const int nrows = Cin * HEAD_ROWS;
+        auto fetch = [&](int r, int px) -> float {
+            const int c = r / HEAD_ROWS, y = ty0 + r % HEAD_ROWS - 1, x = tx0 + px - 1;
+            if (r >= nrows || y < 0 || y >= p.H || x < 0 || x >= p.W) return 0.f;
+            if (c < Cpl) return (__ldg(p.planar_in + (((size_t)s * Cpl + c) * p.H + y) * p.W + x) - mn) * inv;
+            return __ldg(p.noise_map + (size_t)y * p.W + x);
+        };
+        for (int r0 = wrp; r0 < nrows; r0 += 32) {
+            float v0[4], v1[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int ry = tap / 3, sx = tap % 3;
-            for (int c = 0; c < Cin; ++c) {
-                float a = patch[c * 324 + (ty + ry) * 18 + tx + sx];
-                const float4* wp = reinterpret_cast<const float4*>(wts + (tap * Cin + c) * 64 + cb);
+            for (int u = 0; u < 4; ++u) {
+                v0[u] = fetch(r0 + 8 * u, lane);
+                v1[u] = lane < 2 ? fetch(r0 + 8 * u, 32 + lane) : 0.f;
+            }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 b = wp[q];
-                    acc[4 * q + 0] = fmaf(a, b.x, acc[4 * q + 0]);
-                    acc[4 * q + 1] = fmaf(a, b.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(a, b.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(a, b.w, acc[4 * q + 3]);
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + 8 * u;
+                if (r < nrows) {
+                    patch[r * HT_PITCH + lane] = v0[u];
+                    if (lane < 4) patch[r * HT_PITCH + 32 + lane] = v1[u];  // columns 34, 35 are padding (zero)
                 }
             }
         }
+    }
+    for (int t = tid; t < 9 * Cin * 16; t += 256) {  // float4 t = row (tap, c) x 16 quads
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w) + t);
+        const int r = t >> 4, q16 = t & 15;
+        *reinterpret_cast<float4*>(wts + r * HEAD_WPITCH + (q16 >> 2) * 20 + (q16 & 3) * 4) = w;
+    }
+    __syncthreads();
+    const int cbq = tid & 3, tx8 = (tid >> 2) & 7, ty = tid >> 5;
+    float acc[4][16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+    for (int c = 0; c < Cin; ++c) {
+#pragma unroll
+        for (int ry = 0; ry < 3; ++ry) {
+            const float* ar = patch + (c * HEAD_ROWS + ty + ry) * HT_PITCH + 4 * tx8;
+            const float4 a0 = *reinterpret_cast<const float4*>(ar);
+            const float2 a1 = *reinterpret_cast<const float2*>(ar + 4);
+            const float a[6] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y};
+#pragma unroll
+            for (int sx = 0; sx < 3; ++sx) {
+                const float4* wp = reinterpret_cast<const float4*>(wts + ((ry * 3 + sx) * Cin + c) * HEAD_WPITCH + cbq * 20);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b = wp[q];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i][4 * q + 0] = fmaf(a[i + sx], b.x, acc[i][4 * q + 0]);
+                        acc[i][4 * q + 1] = fmaf(a[i + sx], b.y, acc[i][4 * q + 1]);
+                        acc[i][4 * q + 2] = fmaf(a[i + sx], b.z, acc[i][4 * q + 2]);
+                        acc[i][4 * q + 3] = fmaf(a[i + sx], b.w, acc[i][4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    const int y = ty0 + ty;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = tx0 + 4 * tx8 + i;
         if (y < p.H && x < p.W) {
-            const size_t o = (((size_t)s * p.H + y) * p.W + x) * 64 + cb;
+            const size_t o = (((size_t)s * p.H + y) * p.W + x) * 64 + cbq * 16;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                st_act4(p.nhwc, p.nhwc_hi, p.nhwc_lo, o + 4 * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+                st_act4(p.nhwc, p.nhwc_hi, p.nhwc_lo, o + 4 * q, make_float4(acc[i][4 * q], acc[i][4 * q + 1], acc[i][4 * q + 2], acc[i][4 * q + 3]));
         }
     }
 }
@@ -306,56 +347,84 @@ __global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
 // tail: [S][H][W][64] -> planar [S][10][H][W], v = out * range + min folded into the store
 // (PnP_ADMM.m:138,187-192).
 // ---------------------------------------------------------------------------------------
+// Register-blocked like the head: a thread owns 4 consecutive pixels of a row x all 10 outputs, for a quarter of the input
+// channels (kq = tid & 3 takes channels 4 k + kq); the four partial sums of a pixel group meet through two shuffles (fixed order:
+// deterministic), then lane kq stores pixel kq, so a warp writes 32 consecutive pixels of a plane.  CTA = 256 threads = a 32 x 8
+// pixel tile (196 per slice); K = 64 is staged in four chunks of 16 channels.  Patch planes are 10 x 36 floats: 360 = 8 mod 32
+// puts the four kq lanes on different banks.
+constexpr int TAIL_TH = 8, TAIL_ROWS = TAIL_TH + 2, TAIL_PLANE = TAIL_ROWS * HT_PITCH;
 __global__ void __launch_bounds__(256) tail_fp32_kernel(HeadTailParams p) {
-    __shared__ float patch[16][18][18 + 1];
-    __shared__ __align__(16) float wts[9][16][12];
+    __shared__ __align__(16) float patch[16 * TAIL_PLANE];   // [16][10][36]
+    __shared__ __align__(16) float wts[9 * 16 * 12];         // [9][16][12]
     const int tid = threadIdx.x;
-    const int tiles_x = (p.W + 15) / 16;
-    const int ty0 = (blockIdx.x / tiles_x) * 16, tx0 = (blockIdx.x % tiles_x) * 16;
+    const int tiles_x = (p.W + HT_TW - 1) / HT_TW;
+    const int ty0 = (blockIdx.x / tiles_x) * TAIL_TH, tx0 = (blockIdx.x % tiles_x) * HT_TW;
     const int s = blockIdx.z;
-    const int ty = tid >> 4, tx = tid & 15;
     const size_t in_off = (size_t)s * p.H * p.W * 64;
-    float acc[10];
+    const int kq = tid & 3, tx8 = (tid >> 2) & 7, ty = tid >> 5;
+    float acc[4][10];
 #pragma unroll
-    for (int j = 0; j < 10; ++j) acc[j] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
     for (int c0 = 0; c0 < 64; c0 += 16) {
         __syncthreads();
-        for (int t = tid; t < 324 * 4; t += 256) {
+        for (int t = tid; t < TAIL_ROWS * (HT_TW + 2) * 4; t += 256) {
             int pix = t >> 2, q = t & 3;
-            int py = pix / 18, px = pix % 18;
+            int py = pix / (HT_TW + 2), px = pix % (HT_TW + 2);
             int y = ty0 + py - 1, x = tx0 + px - 1;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (y >= 0 && y < p.H && x >= 0 && x < p.W)
                 v = ld_act4(p.nhwc, p.nhwc_hi, p.nhwc_lo, in_off + ((size_t)y * p.W + x) * 64 + c0 + 4 * q);
-            patch[4 * q + 0][py][px] = v.x;
-            patch[4 * q + 1][py][px] = v.y;
-            patch[4 * q + 2][py][px] = v.z;
-            patch[4 * q + 3][py][px] = v.w;
+            float* d = patch + (4 * q) * TAIL_PLANE + py * HT_PITCH + px;
+            d[0] = v.x;
+            d[TAIL_PLANE] = v.y;
+            d[2 * TAIL_PLANE] = v.z;
+            d[3 * TAIL_PLANE] = v.w;
         }
         for (int t = tid; t < 9 * 16 * 12; t += 256) {
             int tap = t / 192, r = t % 192;
             int k = r / 12, co = r % 12;
-            wts[tap][k][co] = co < 10 ? __ldg(p.w + ((size_t)tap * 64 + c0 + k) * 10 + co) : 0.f;
+            wts[t] = co < 10 ? __ldg(p.w + ((size_t)tap * 64 + c0 + k) * 10 + co) : 0.f;
         }
         __syncthreads();
+#pragma unroll 1
+        for (int k4 = 0; k4 < 4; ++k4) {
+            const int ch = 4 * k4 + kq;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int ry = tap / 3, sx = tap % 3;
+            for (int ry = 0; ry < 3; ++ry) {
+                const float* ar = patch + ch * TAIL_PLANE + (ty + ry) * HT_PITCH + 4 * tx8;
+                const float4 a0 = *reinterpret_cast<const float4*>(ar);
+                const float2 a1 = *reinterpret_cast<const float2*>(ar + 4);
+                const float a[6] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y};
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                float a = patch[k][ty + ry][tx + sx];
-                float4 b0 = *reinterpret_cast<const float4*>(&wts[tap][k][0]);
-                float4 b1 = *reinterpret_cast<const float4*>(&wts[tap][k][4]);
-                float2 b2 = *reinterpret_cast<const float2*>(&wts[tap][k][8]);
-                acc[0] = fmaf(a, b0.x, acc[0]); acc[1] = fmaf(a, b0.y, acc[1]);
-                acc[2] = fmaf(a, b0.z, acc[2]); acc[3] = fmaf(a, b0.w, acc[3]);
-                acc[4] = fmaf(a, b1.x, acc[4]); acc[5] = fmaf(a, b1.y, acc[5]);
-                acc[6] = fmaf(a, b1.z, acc[6]); acc[7] = fmaf(a, b1.w, acc[7]);
-                acc[8] = fmaf(a, b2.x, acc[8]); acc[9] = fmaf(a, b2.y, acc[9]);
+                for (int sx = 0; sx < 3; ++sx) {
+                    const float* wp = wts + ((ry * 3 + sx) * 16 + ch) * 12;
+                    const float4 b0 = *reinterpret_cast<const float4*>(wp);
+                    const float4 b1 = *reinterpret_cast<const float4*>(wp + 4);
+                    const float2 b2 = *reinterpret_cast<const float2*>(wp + 8);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float av = a[i + sx];
+                        acc[i][0] = fmaf(av, b0.x, acc[i][0]); acc[i][1] = fmaf(av, b0.y, acc[i][1]);
+                        acc[i][2] = fmaf(av, b0.z, acc[i][2]); acc[i][3] = fmaf(av, b0.w, acc[i][3]);
+                        acc[i][4] = fmaf(av, b1.x, acc[i][4]); acc[i][5] = fmaf(av, b1.y, acc[i][5]);
+                        acc[i][6] = fmaf(av, b1.z, acc[i][6]); acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+                        acc[i][8] = fmaf(av, b2.x, acc[i][8]); acc[i][9] = fmaf(av, b2.y, acc[i][9]);
+                    }
+                }
             }
         }
     }
-    const int y = ty0 + ty, x = tx0 + tx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 1);
+            acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 2);
+        }
+    const int y = ty0 + ty, x = tx0 + 4 * tx8 + kq;  // all four lanes hold all sums; lane kq stores pixel kq
     if (y < p.H && x < p.W) {
         float mn = 0.f, rg = 1.f;
         if (p.minmax) {
@@ -363,8 +432,10 @@ __global__ void __launch_bounds__(256) tail_fp32_kernel(HeadTailParams p) {
             rg = p.minmax[2 * s + 1] - mn;
         }
 #pragma unroll
-        for (int j = 0; j < 10; ++j)
-            p.planar_out[(((size_t)s * 10 + j) * p.H + y) * p.W + x] = acc[j] * rg + mn;
+        for (int j = 0; j < 10; ++j) {
+            const float v = kq == 0 ? acc[0][j] : kq == 1 ? acc[1][j] : kq == 2 ? acc[2][j] : acc[3][j];
+            p.planar_out[(((size_t)s * 10 + j) * p.H + y) * p.W + x] = v * rg + mn;
+        }
     }
 }
 
@@ -401,20 +472,20 @@ int resample_fp32(qmri_ctx* ctx, const ConvParams& p) {
 }
 
 int head_fp32(qmri_ctx* ctx, const HeadTailParams& p) {
-    size_t smem = (size_t)(p.Cin * 324 + 9 * p.Cin * 64) * sizeof(float);
+    size_t smem = (size_t)(p.Cin * HEAD_ROWS * HT_PITCH + 9 * p.Cin * HEAD_WPITCH) * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         QCUDA(cudaFuncSetAttribute(head_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid(((p.H + 15) / 16) * ((p.W + 15) / 16), 1, p.S);
+    dim3 grid(((p.H + HEAD_TH - 1) / HEAD_TH) * ((p.W + HT_TW - 1) / HT_TW), 1, p.S);
     head_fp32_kernel<<<grid, 256, smem, ctx->stream>>>(p);
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
 }
 
 int tail_fp32(qmri_ctx* ctx, const HeadTailParams& p) {
-    dim3 grid(((p.H + 15) / 16) * ((p.W + 15) / 16), 1, p.S);
+    dim3 grid(((p.H + TAIL_TH - 1) / TAIL_TH) * ((p.W + HT_TW - 1) / HT_TW), 1, p.S);
     tail_fp32_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
