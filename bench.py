@@ -42,6 +42,14 @@ RHO = 0.05
 FLOPS_PER_SLICE_FWD = 213.25e9
 
 
+def load_traffic():
+    """DRAM bytes per unit of work from the committed ncu captures (profiles/traffic.json; how each was taken is in the file)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -295,8 +303,12 @@ def run_ours(args, rank, world, local_rank):
     ms_fwd, n_fwd_launch = timed(fwd, 5, 3)
     fwd_tflops = net.flops(S, N_IMG, N_IMG) * 5 / (ms_fwd * 1e-3) / 1e12
     tensor_peak = peaks["bf16_tflops_sustained"]
+    traffic = load_traffic()
+    t_fwd = traffic.get(f"unetres_forward_S{S}")
     roofline = {"bound": "tensor", "kernel": "UNetRes forward (64 conv launches; 3x3 convs = 97% of flops)", "achieved": fwd_tflops,
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": fwd_tflops / tensor_peak, "traffic": None,
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": fwd_tflops / tensor_peak,
+                "traffic": (t_fwd["dram_read_bytes"] + t_fwd["dram_write_bytes"]) if t_fwd else None,
+                "traffic_note": (t_fwd or {}).get("how", "no committed ncu capture for this slice count"),
                 "peak_source": f"{peaks['src']} dense bf16 (sustained); the fp32 exact mode runs on CUDA cores, see DESIGN.md",
                 "ms_per_forward": ms_fwd / 5, "precision_mode": args.precision}
     # K1 at a batch larger than L2 (algorithmic bytes: 20 B per pixel-channel per iteration)
@@ -312,8 +324,13 @@ def run_ours(args, rank, world, local_rank):
         ms_k1, _ = timed(lambda: sess1.xupdate_only(reps), 3, 2, collective=False)
         t_launch = ms_k1 * 1e-3 / (3 * reps)
         gbs = 20.0 * hw * C_CH * S1 / t_launch / 1e9
-        roof_k1 = {"bound": "hbm", "kernel": "xupdate_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": gbs / peaks["hbm_gbs"], "traffic": None, "slices": S1, "us_per_slice_iteration": 1e6 * t_launch / S1,
+        t_k1 = traffic.get(f"k1_xupdate_S{S1}")
+        roof_k1 = {"bound": "hbm", "kernel": "x-update = stream_fwd_kernel + stream_solve_kernel + stream_adj_kernel (3 launches; the single cluster "
+                                             "kernel xupdate_kernel serves one-slice batches)",
+                   "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": gbs / peaks["hbm_gbs"], "traffic": (t_k1["dram_read_bytes"] + t_k1["dram_write_bytes"]) if t_k1 else None,
+                   "traffic_note": (t_k1 or {}).get("how", "no committed ncu capture for this slice count"),
+                   "slices": S1, "us_per_slice_iteration": 1e6 * t_launch / S1,
                    "algorithmic_bytes_per_launch": 20 * hw * C_CH * S1}
         sess1.close()
         # K2: one slice against a 100k-atom dictionary, complex data (40 flop per px-atom)
