@@ -96,7 +96,7 @@ static inline uint32_t p4_entry(int k2, int k1, int j, bool last) {
 }
 
 
-constexpr int STREAM_QMAX = 24;      // == k1::QMAX_STREAM
+constexpr int STREAM_QMAX = 64;      // == k1::QMAX_STREAM
 constexpr int STREAM_OVF_MAX = 96;   // == k1::OVF_MAX_STREAM
 
 // Work items of the streaming kernel.  The samples of a k-space row k1 are cut into chunks of at most Q samples (Q = the
@@ -247,6 +247,98 @@ static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>
     for (int i = 0; i < N; ++i) {
         t.tw[2 * i] = (float)cos(-2.0 * PI * i / N);
         t.tw[2 * i + 1] = (float)sin(-2.0 * PI * i / N);
+    }
+}
+
+// ---- general V ------------------------------------------------------------------------------------
+// P = vertical stack of S_i kron(conj(V(i,:)), I): frame i samples sum_c V(i,c) X^_c on its own mask Omega_i.  The normal matrix
+// is block diagonal in k-space: at location k the C x C block G_k = sum_{i: k in Omega_i} V(i,:)^T V(i,:).  All channels are
+// therefore transformed on the UNION of the masks (one shared work-item table), and small per-location kernels mix channels.
+struct GeneralTables {
+    int L = 0, C = 0, nU = 0;
+    std::vector<int32_t> ulist;        // [nU] union of the sampled locations, ascending k = k1 + N k2
+    std::vector<int32_t> memb_ptr;     // [nU + 1] CSR over union locations
+    std::vector<int32_t> memb_frame;   // [nmeas] frame i of each (location, frame) incidence
+    std::vector<int32_t> memb_meas;    // [nmeas] its row in y (frame-major measurement index)
+    std::vector<int32_t> meas_u;       // [nmeas] union slot of measurement j
+    std::vector<int32_t> meas_frame;   // [nmeas] frame of measurement j
+    std::vector<float> V;              // [L][C] row-major
+    K1Tables tu;                       // streaming-kernel tables of the single pseudo-frame "union"
+};
+
+static inline void build_general_tables(int N, const std::vector<std::vector<int32_t>>& frames, const double* Vcm /*L x C col-major*/,
+                                        int L, int C, GeneralTables& g, int stream_q_min = 1) {
+    g.L = L;
+    g.C = C;
+    g.V.resize((size_t)L * C);
+    for (int i = 0; i < L; ++i)
+        for (int c = 0; c < C; ++c) g.V[(size_t)i * C + c] = (float)Vcm[i + (size_t)L * c];
+    std::vector<uint8_t> seen((size_t)N * N, 0);
+    for (const auto& f : frames)
+        for (int32_t k : f) seen[k] = 1;
+    g.ulist.clear();
+    std::vector<int32_t> slot((size_t)N * N, -1);
+    for (int k = 0; k < N * N; ++k)
+        if (seen[k]) {
+            slot[k] = (int32_t)g.ulist.size();
+            g.ulist.push_back(k);
+        }
+    g.nU = (int)g.ulist.size();
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> inc(g.nU);
+    g.meas_u.clear();
+    g.meas_frame.clear();
+    int32_t j = 0;
+    for (int i = 0; i < L; ++i)
+        for (int32_t k : frames[i]) {
+            inc[slot[k]].push_back({i, j});
+            g.meas_u.push_back(slot[k]);
+            g.meas_frame.push_back(i);
+            ++j;
+        }
+    g.memb_ptr.assign(g.nU + 1, 0);
+    g.memb_frame.clear();
+    g.memb_meas.clear();
+    for (int u = 0; u < g.nU; ++u) {
+        for (auto& e : inc[u]) {
+            g.memb_frame.push_back(e.first);
+            g.memb_meas.push_back(e.second);
+        }
+        g.memb_ptr[u + 1] = (int32_t)g.memb_frame.size();
+    }
+    std::vector<std::vector<int32_t>> one(1, g.ulist);
+    build_k1_tables(N, one, g.tu, stream_q_min);
+}
+
+// (G_u + rho I)^{-1} for every union location, row-major C x C, computed in double (Gauss-Jordan with partial pivoting on an SPD matrix)
+static inline void general_inverses(const GeneralTables& g, double rho, std::vector<float>& Minv) {
+    const int C = g.C;
+    Minv.assign((size_t)g.nU * C * C, 0.f);
+    std::vector<double> A((size_t)C * 2 * C);
+    for (int u = 0; u < g.nU; ++u) {
+        for (int r = 0; r < C; ++r)
+            for (int c = 0; c < 2 * C; ++c) A[(size_t)r * 2 * C + c] = (c == r ? rho : 0.0) + (c == C + r ? 1.0 : 0.0);
+        for (int e = g.memb_ptr[u]; e < g.memb_ptr[u + 1]; ++e) {
+            const float* v = &g.V[(size_t)g.memb_frame[e] * C];
+            for (int r = 0; r < C; ++r)
+                for (int c = 0; c < C; ++c) A[(size_t)r * 2 * C + c] += (double)v[r] * (double)v[c];
+        }
+        for (int col = 0; col < C; ++col) {
+            int piv = col;
+            for (int r = col + 1; r < C; ++r)
+                if (fabs(A[(size_t)r * 2 * C + col]) > fabs(A[(size_t)piv * 2 * C + col])) piv = r;
+            if (piv != col)
+                for (int c = 0; c < 2 * C; ++c) std::swap(A[(size_t)piv * 2 * C + c], A[(size_t)col * 2 * C + c]);
+            const double d = 1.0 / A[(size_t)col * 2 * C + col];
+            for (int c = 0; c < 2 * C; ++c) A[(size_t)col * 2 * C + c] *= d;
+            for (int r = 0; r < C; ++r) {
+                if (r == col) continue;
+                const double f = A[(size_t)r * 2 * C + col];
+                if (f != 0.0)
+                    for (int c = 0; c < 2 * C; ++c) A[(size_t)r * 2 * C + c] -= f * A[(size_t)col * 2 * C + c];
+            }
+        }
+        for (int r = 0; r < C; ++r)
+            for (int c = 0; c < C; ++c) Minv[((size_t)u * C + r) * C + c] = (float)A[(size_t)r * 2 * C + C + c];
     }
 }
 

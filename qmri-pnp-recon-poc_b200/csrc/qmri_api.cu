@@ -242,6 +242,14 @@ struct qmri_op {
     uint32_t* d_ent = nullptr;
     uint16_t* d_rowmask = nullptr;
     int k1_kernel = 0;  // 0 = choose by batch size, 1 = cluster kernel, 2 = streaming kernel (QMRI_K1_KERNEL=cluster|stream)
+    // general V (not the identity): channels are transformed on the union of the masks and mixed per k-space location
+    bool general = false;
+    optab::GeneralTables g;
+    float* d_V = nullptr;
+    int *d_memb_ptr = nullptr, *d_memb_frame = nullptr, *d_memb_meas = nullptr, *d_meas_u = nullptr, *d_meas_frame = nullptr;
+    float* d_minv = nullptr;      // [nU][C][C] (G_u + rho I)^{-1} for minv_rho
+    double minv_rho = -1.0;
+    const optab::K1Tables& stream_tables() const { return general ? g.tu : t; }
     // scratch for the host entry points
     DevBuf stage, a_re, a_im, b_re, b_im, c_re, c_im, ybuf, mm_ord, mm_f;
     DevBuf k1_part, k1_cbuf;  // streaming x-update: partial sample sums / solved samples
@@ -254,13 +262,18 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     if (N != 224 || M != 224)
         return qmri_fail(QMRI_EUNSUPPORTED, "this build supports N == M == 224 only (got %d x %d)", N, M);
     if (C < 1 || C > 64) return qmri_fail(QMRI_EINVAL, "C = %d out of range", C);
-    if (L != C) return qmri_fail(QMRI_EUNSUPPORTED, "unsupported V: %d x %d; this build needs V == eye(C) (SURVEY.md 8f-2)", L, C);
-    if (V) {
-        for (int i = 0; i < L; ++i)
+    bool identity = (L == C);
+    if (V && identity) {
+        for (int i = 0; i < L && identity; ++i)
             for (int c = 0; c < C; ++c)
-                if (fabs(V[i + (size_t)L * c] - (i == c ? 1.0 : 0.0)) > 1e-12)
-                    return qmri_fail(QMRI_EUNSUPPORTED, "unsupported V: not the identity at (%d,%d); general V is SURVEY.md 8f-2", i + 1, c + 1);
+                if (fabs(V[i + (size_t)L * c] - (i == c ? 1.0 : 0.0)) > 1e-12) {
+                    identity = false;
+                    break;
+                }
     }
+    if (!identity && !V) return qmri_fail(QMRI_EINVAL, "operator: V must be given when size(V,1) != C");
+    if (!identity && C > 16) return qmri_fail(QMRI_EUNSUPPORTED, "general V: at most 16 channels (got %d)", C);
+    if ((int)frames.size() != L) return qmri_fail(QMRI_EINVAL, "operator: %zu frames for size(V,1) = %d", frames.size(), L);
     for (int f = 0; f < L; ++f) {
         if (frames[f].size() > 4096) return qmri_fail(QMRI_EUNSUPPORTED, "frame %d samples %zu k-space locations; limit 4096", f, frames[f].size());
         for (size_t j = 0; j < frames[f].size(); ++j) {
@@ -278,12 +291,23 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     if (env && !strcmp(env, "cluster")) op->k1_kernel = 1;
     if (env && !strcmp(env, "stream")) op->k1_kernel = 2;
     env = getenv("QMRI_K1_QMIN");  // tuning knob: smallest chunk size tried for the streaming kernel's work items
-    optab::build_k1_tables(N, frames, op->t, env ? atoi(env) : 8);  // 8: measured best on the spiral masks (fewer overflow partials)
-    const optab::K1Tables& t = op->t;
+    const int q_min = env ? atoi(env) : 8;  // 8: measured best on the spiral masks (fewer overflow partials)
+    optab::build_k1_tables(N, frames, op->t, q_min);
+    op->general = !identity;
+    if (op->general) {
+        optab::build_general_tables(N, frames, V, L, C, op->g, q_min);
+        if (!op->g.tu.stream_ok || op->g.nU > 4096) {
+            const int nU = op->g.nU;
+            delete op;
+            return qmri_fail(QMRI_EUNSUPPORTED, "general V: the union of the %d masks holds %d k-space locations; this build handles up to 4096 "
+                             "(about 15 spiral frames) - SURVEY.md 8f-2", L, nU);
+        }
+    }
+    const optab::K1Tables& t = op->stream_tables();  // device tables: per-frame masks (V = I) or the union mask (general V)
     size_t nm = std::max(1, t.nmeas);
     int r = 0;
     r |= dev_alloc(&op->d_tw, (size_t)N);
-    r |= dev_alloc(&op->d_frame_ptr, (size_t)C + 1);
+    r |= dev_alloc(&op->d_frame_ptr, t.frame_ptr.size());
     r |= dev_alloc(&op->d_samp, nm);
     r |= dev_alloc(&op->d_p4tab, std::max<size_t>(t.p4tab.size(), 1));
     r |= dev_alloc(&op->d_tw2, (size_t)256);
@@ -292,12 +316,31 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     r |= dev_alloc(&op->d_itB, t.itB.size());
     r |= dev_alloc(&op->d_ent, t.ent.size());
     r |= dev_alloc(&op->d_rowmask, t.rowmask.size());
+    if (op->general) {
+        const optab::GeneralTables& g = op->g;
+        const size_t nmf = std::max<size_t>(g.memb_frame.size(), 1);
+        r |= dev_alloc(&op->d_V, g.V.size());
+        r |= dev_alloc(&op->d_memb_ptr, g.memb_ptr.size());
+        r |= dev_alloc(&op->d_memb_frame, nmf);
+        r |= dev_alloc(&op->d_memb_meas, nmf);
+        r |= dev_alloc(&op->d_meas_u, nmf);
+        r |= dev_alloc(&op->d_meas_frame, nmf);
+        r |= dev_alloc(&op->d_minv, std::max<size_t>((size_t)g.nU * C * C, 1));
+        if (!r) {
+            cudaMemcpy(op->d_V, g.V.data(), sizeof(float) * g.V.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(op->d_memb_ptr, g.memb_ptr.data(), sizeof(int) * g.memb_ptr.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(op->d_memb_frame, g.memb_frame.data(), sizeof(int) * g.memb_frame.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(op->d_memb_meas, g.memb_meas.data(), sizeof(int) * g.memb_meas.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(op->d_meas_u, g.meas_u.data(), sizeof(int) * g.meas_u.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(op->d_meas_frame, g.meas_frame.data(), sizeof(int) * g.meas_frame.size(), cudaMemcpyHostToDevice);
+        }
+    }
     if (r) {
         qmri_op_destroy(op);
         return QMRI_ENOMEM;
     }
     cudaMemcpy(op->d_tw, t.tw.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice);
-    cudaMemcpy(op->d_frame_ptr, t.frame_ptr.data(), sizeof(int) * (C + 1), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_frame_ptr, t.frame_ptr.data(), sizeof(int) * t.frame_ptr.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_samp, t.samp.data(), sizeof(uint16_t) * t.nmeas, cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_tw2, t.tw2.data(), sizeof(float) * t.tw2.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_tw448, t.tw448.data(), sizeof(float) * t.tw448.size(), cudaMemcpyHostToDevice);
@@ -343,6 +386,8 @@ extern "C" int qmri_op_destroy(qmri_op* op) {
     cudaStreamSynchronize(op->ctx->stream);
     cudaFree(op->d_tw); cudaFree(op->d_frame_ptr); cudaFree(op->d_samp);
     cudaFree(op->d_p4tab);
+    cudaFree(op->d_V); cudaFree(op->d_memb_ptr); cudaFree(op->d_memb_frame); cudaFree(op->d_memb_meas); cudaFree(op->d_meas_u);
+    cudaFree(op->d_meas_frame); cudaFree(op->d_minv);
     cudaFree(op->d_tw2); cudaFree(op->d_tw448); cudaFree(op->d_itA); cudaFree(op->d_itB); cudaFree(op->d_ent); cudaFree(op->d_rowmask);
     op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
     op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
@@ -365,10 +410,52 @@ extern "C" int qmri_op_indices(const qmri_op* op, int32_t* idx, int64_t* frame_p
 // 7.4 us at eight, 6.97 vs 4.37 us per slice at 120.  QMRI_K1_KERNEL=cluster|stream forces one (tests, profiling).
 // part / cbuf: scratch of the streaming kernels.  The host entry points use the operator's; an ADMM session brings its own,
 // sized once for its batch, because its CUDA graph keeps the addresses.
+// General V: forward transform of every channel on the union mask -> per-location channel mixing -> adjoint transform.
+static int k1_general_dispatch(qmri_op* op, K1Params p, int S, DevBuf* part, DevBuf* cbuf) {
+    qmri_ctx* ctx = op->ctx;
+    const optab::GeneralTables& g = op->g;
+    const int nU = g.nU;
+    p.shared_mask = 1;
+    p.G = k1_stream_groups(S, op->C, ctx->sm_count);
+    QCHECK(part->ensure(std::max<size_t>(k1_stream_part_elems(S, op->C, p.G, nU), 1) * sizeof(float2)));
+    QCHECK(cbuf->ensure(std::max<size_t>(k1_stream_cbuf_elems(S, op->C, nU), 1) * sizeof(float2)));
+    p.part = part->as<float2>();
+    p.cbuf = cbuf->as<float2>();
+    GeneralMix m = {};
+    m.part = p.part; m.cbuf = p.cbuf; m.y = p.y; m.y_out = p.y_out;
+    m.V = op->d_V; m.Minv = op->d_minv;
+    m.memb_ptr = op->d_memb_ptr; m.memb_frame = op->d_memb_frame; m.memb_meas = op->d_memb_meas;
+    m.meas_u = op->d_meas_u; m.meas_frame = op->d_meas_frame;
+    m.S = S; m.C = op->C; m.L = op->L; m.G = p.G; m.nU = nU; m.nmeas = op->t.nmeas;
+    if (p.mode == K1_FORWARD) {
+        p.stage = K1_STAGE_FWD_ONLY;
+        QCHECK(k1_stream_launch(ctx, p, S, nU));
+        return k1_general_mix_forward(ctx, m);
+    }
+    if (p.mode == K1_ADJOINT) {
+        QCHECK(k1_general_mix_adjoint(ctx, m));
+        return k1_stream_launch(ctx, p, S, nU);
+    }
+    if (!(p.rho > 0.0)) return qmri_fail(QMRI_EINVAL, "x-update: rho must be positive");
+    if (op->minv_rho != p.rho) {  // happens on the first x-update of a run, i.e. before any CUDA-graph capture of the loop
+        std::vector<float> minv;
+        optab::general_inverses(g, p.rho, minv);
+        QCUDA(cudaStreamSynchronize(ctx->stream));
+        QCUDA(cudaMemcpy(op->d_minv, minv.data(), sizeof(float) * minv.size(), cudaMemcpyHostToDevice));
+        op->minv_rho = p.rho;
+    }
+    p.stage = K1_STAGE_FWD_ONLY;
+    QCHECK(k1_stream_launch(ctx, p, S, nU));
+    QCHECK(k1_general_mix_solve(ctx, m));
+    p.stage = K1_STAGE_ADJ_ONLY;
+    return k1_stream_launch(ctx, p, S, nU);
+}
+
 static int k1_dispatch(qmri_op* op, const K1Params& p_in, int S, DevBuf* part = nullptr, DevBuf* cbuf = nullptr) {
     K1Params p = p_in;
     if (!part) part = &op->k1_part;
     if (!cbuf) cbuf = &op->k1_cbuf;
+    if (op->general) return k1_general_dispatch(op, p, S, part, cbuf);
     qmri_ctx* ctx = op->ctx;
     const bool can_stream = op->t.stream_ok;
     bool stream = can_stream && (long long)S * op->C * K1_STREAM_MIN_IMAGES_DIV >= (long long)ctx->sm_count;
@@ -402,7 +489,7 @@ static void k1_fill_tables(const qmri_op* op, K1Params& p) {
     p.itB = op->d_itB;
     p.ent = op->d_ent;
     p.rowmask = op->d_rowmask;
-    p.n_ovf = op->t.n_ovf;
+    p.n_ovf = op->stream_tables().n_ovf;
     p.C = op->C;
     p.nmeas = op->t.nmeas;
 }
@@ -515,6 +602,7 @@ extern "C" int qmri_xupdate(qmri_op* op, double rho, const void* y, int y_dtype,
     p.y = op->ybuf.as<float2>();
     p.out_re = ar; p.out_im = ai;                                                // a = x
     p.inv_1p_rho = (float)(1.0 / (1.0 + rho));
+    p.rho = rho;
     QCHECK(k1_dispatch(op, p, S));
     QCHECK(image_download(op, x, x_dtype, S, ar, ai));
     if (w || minmax) {
@@ -723,6 +811,9 @@ extern "C" int qmri_admm_upload(qmri_admm* st, const void* y, int y_dtype, const
     }
     QCUDA(cudaMemcpyAsync(op->stage.p, x0, n * dtype_size(x0_dtype), cudaMemcpyHostToDevice, ctx->stream));
     QCHECK(unpack_async(ctx, op->stage.p, x0_dtype, st->x0_re.as<float>(), st->x0_im.as<float>(), n));
+    // w starts as X0 so that qmri_admm_xupdate_only (profiling) has a defined state before the first qmri_admm_run
+    QCUDA(cudaMemcpyAsync(st->w_re.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    QCUDA(cudaMemcpyAsync(st->w_im.p, st->x0_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     st->uploaded = true;
     return QMRI_OK;
 }
@@ -742,6 +833,7 @@ static int admm_k1(qmri_admm* st, bool write_x) {
     p.y = st->y.as<float2>();
     p.minmax = st->mm_ord.as<int>();
     p.inv_1p_rho = (float)(1.0 / (1.0 + st->prm.gamma));
+    p.rho = st->prm.gamma;
     return k1_dispatch(op, p, st->S, &st->k1_part, &st->k1_cbuf);
 }
 
@@ -789,18 +881,30 @@ extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
     DevSetter ds(ctx->device);
     const int S = st->S;
     const size_t n = op->plane() * S;
-    // x = v = X0, uold = 0 (PnP_ADMM.m:76-78): w_1 = x_1 + u_0 = X0 because A X0 = y makes iteration 1's solve a no-op
-    QCUDA(cudaMemcpyAsync(st->w_re.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    QCUDA(cudaMemcpyAsync(st->w_im.p, st->x0_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    // x = v = X0, uold = 0 (PnP_ADMM.m:76-78); zero iterations return X0
     QCUDA(cudaMemcpyAsync(st->x_re.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     QCUDA(cudaMemcpyAsync(st->x_im.p, st->x0_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     QCHECK(k1_minmax_init(ctx, st->mm_ord.as<int>(), S));
     auto iteration = [&](int k) -> int {
         if (k == 0) {
-            dim3 grid(std::min<unsigned>(nblk(op->plane()), 256), S);
-            add_minmax_kernel<<<grid, 256, 0, ctx->stream>>>(st->w_re.as<float>(), st->w_im.as<float>(), nullptr, nullptr, nullptr,
-                                                            nullptr, op->plane(), st->mm_ord.as<int>());
-            QLAUNCH_CHECK(ctx);
+            // Iteration 1 of PnP_ADMM.m:102 with v = X0, u = 0: x_1 = argmin |y - A x|^2 + rho |x - X0|^2, w_1 = x_1 + u_0 = x_1.
+            // (For X0 = A^H y and A A^H = I this returns X0 itself - the reference driver's case - but param.X0 is the caller's.)
+            K1Params p = {};
+            k1_fill_tables(op, p);
+            p.mode = K1_SOLVE;
+            p.in_re = st->x0_re.as<float>();
+            p.in_im = st->x0_im.as<float>();
+            p.out_re = st->w_re.as<float>();
+            p.out_im = st->w_im.as<float>();
+            p.y = st->y.as<float2>();
+            p.minmax = st->mm_ord.as<int>();
+            p.inv_1p_rho = (float)(1.0 / (1.0 + st->prm.gamma));
+            p.rho = st->prm.gamma;
+            QCHECK(k1_dispatch(op, p, S, &st->k1_part, &st->k1_cbuf));
+            if (iters == 1) {  // x_1 is the result
+                QCUDA(cudaMemcpyAsync(st->x_re.p, st->w_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                QCUDA(cudaMemcpyAsync(st->x_im.p, st->w_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
         } else {
             QCHECK(admm_k1(st, k == iters - 1));
         }

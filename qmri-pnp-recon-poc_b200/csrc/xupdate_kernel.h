@@ -8,6 +8,7 @@ struct qmri_ctx;
 constexpr int K1_PHASES = 8;  // == optab::K1_PHASES
 
 enum { K1_ADMM = 0, K1_SOLVE = 1, K1_FORWARD = 2, K1_ADJOINT = 3 };
+enum { K1_STAGE_FWD_ONLY = 1, K1_STAGE_ADJ_ONLY = 2 };
 
 struct K1Params {
     // planar fp32 images [S][C][M][N] (n fastest - the MATLAB layout of an N x M x C x S array)
@@ -37,6 +38,8 @@ struct K1Params {
     int n_ovf;               // overflow partials per frame (sizes the shared-memory slots)
     float2* part;            // scratch [S][C][G][ns_max] partial sample sums of the forward kernel
     float2* cbuf;            // scratch [S][C][ns_max]    c = (y - A z) / (1 + rho)
+    int stage;               // general V: K1_STAGE_FWD_ONLY / K1_STAGE_ADJ_ONLY run one half of the streaming path (0 = both)
+    int shared_mask;         // general V: every channel is transformed on the same (union) mask - tables of "frame" 0, cbuf in all modes
     int G;                   // slab groups (CTAs) per image: 2, 4, 8 or 16
     int slabs_per_cta;       // 16 / G (set by k1_stream_launch)
     int C;
@@ -44,6 +47,7 @@ struct K1Params {
     int ns_max;              // largest per-frame sample count (sizes the shared-memory tables; set by k1_launch)
     int mode;
     float inv_1p_rho;
+    double rho;              // host side only (general V: selects the precomputed (G_k + rho I)^{-1})
 };
 
 int k1_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max, int mc);
@@ -54,3 +58,22 @@ size_t k1_stream_part_elems(int S, int C, int G, int ns_max);
 size_t k1_stream_cbuf_elems(int S, int C, int ns_max);
 int k1_stream_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max);
 int k1_minmax_init(qmri_ctx* ctx, int* minmax, int S);
+
+// general V: the per-location kernels that mix channels around the streaming transforms (xupdate_general.cu)
+struct GeneralMix {
+    const float2* part;      // [S][C][G][nU] partial sums of the forward transform on the union (stream_fwd_kernel)
+    float2* cbuf;            // [S][C][nU]    input of the adjoint transform (stream_adj_kernel)
+    const float2* y;         // [S][nmeas]
+    float2* y_out;           // [S][nmeas]
+    const float* V;          // [L][C]
+    const float* Minv;       // [nU][C][C]  (G_u + rho I)^{-1}
+    const int* memb_ptr;     // [nU + 1]
+    const int* memb_frame;   // [nmeas]
+    const int* memb_meas;    // [nmeas]
+    const int* meas_u;       // [nmeas]
+    const int* meas_frame;   // [nmeas]
+    int S, C, L, G, nU, nmeas;
+};
+int k1_general_mix_forward(qmri_ctx* ctx, const GeneralMix& m);   // y_i(k) = sum_c V(i,c) Z^_c(k)
+int k1_general_mix_adjoint(qmri_ctx* ctx, const GeneralMix& m);   // cbuf_c(k) = sum_{i: k in Omega_i} V(i,c) y_i(k)
+int k1_general_mix_solve(qmri_ctx* ctx, const GeneralMix& m);     // cbuf(k) = (G_k + rho I)^{-1} sum_i V(i,:)^T (y_i(k) - V(i,:) Z^(k))

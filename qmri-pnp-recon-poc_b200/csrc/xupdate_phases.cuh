@@ -224,7 +224,7 @@ QHD void sparse_idft_flat(float2* col, const float2* c, const float2* twp, const
 //    twiddle (t <- t * e^{-+2 pi i k2 / 224}), so the inner loops touch no shared memory.
 // tw2[i][j] = e^{-2 pi i (i j) / 224}, i, j < 16: stage twiddles, lanes contiguous in j.
 // =====================================================================================
-constexpr int QMAX_STREAM = 24;      // most samples one work item may carry
+constexpr int QMAX_STREAM = 64;      // most samples one work item may carry
 constexpr int OVF_MAX_STREAM = 96;   // most overflow partials (row chunks beyond the first) per frame
 
 // A shared-memory load the compiler keeps in program order (device code): 15 twiddles fetched ahead of their use on top of

@@ -68,8 +68,9 @@ __global__ void __launch_bounds__(THREADS, 4) stream_fwd_kernel(K1Params p) {
 
     const int tid = threadIdx.x;
     const int g = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
-    const int f0 = p.frame_ptr[c];
-    const int ns = p.frame_ptr[c + 1] - f0;
+    const int ct = p.shared_mask ? 0 : c;  // table row: the channel's own frame, or the shared union mask (general V)
+    const int f0 = p.frame_ptr[ct];
+    const int ns = p.frame_ptr[ct + 1] - f0;
     const size_t img = ((size_t)s * p.C + c) * (size_t)(NF * NF);
 
     for (int i = tid; i < 256; i += THREADS) tw2[i] = p.tw2[i];
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(THREADS, 4) stream_fwd_kernel(K1Params p) {
         s_ent[i] = p.ent[f0 + i];
         pc[i] = make_float2(0.f, 0.f);
     }
-    const uint32_t itA = p.itA[(size_t)c * NF + tid];
+    const uint32_t itA = p.itA[(size_t)ct * NF + tid];
     const int l16 = tid & 15;
     const int col = tid >> 4;
     float2* colp = ws + col * CS;
@@ -164,24 +165,25 @@ __global__ void __launch_bounds__(THREADS, 4) stream_adj_kernel(K1Params p) {
 
     const int tid = threadIdx.x;
     const int g = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
-    const int f0 = p.frame_ptr[c];
-    const int ns = p.frame_ptr[c + 1] - f0;
+    const int ct = p.shared_mask ? 0 : c;
+    const int f0 = p.frame_ptr[ct];
+    const int ns = p.frame_ptr[ct + 1] - f0;
     const size_t img = ((size_t)s * p.C + c) * (size_t)(NF * NF);
 
     for (int i = tid; i < 256; i += THREADS) tw2[i] = p.tw2[i];
     for (int i = tid; i < 2 * NF; i += THREADS) tw448[i] = p.tw448[i];
     for (int i = tid; i < ns; i += THREADS) {
         s_ent[i] = p.ent[f0 + i];
-        if (MODE == K1_ADJOINT) {
+        if (MODE == K1_ADJOINT && !p.shared_mask) {
             const float2 y = p.y[(size_t)s * p.nmeas + f0 + i];
             pc[i] = make_float2(y.x * (1.0f / (float)NF), y.y * (1.0f / (float)NF));
         } else {
             pc[i] = p.cbuf[((size_t)s * p.C + c) * p.ns_max + i];
         }
     }
-    const uint32_t itA = p.itA[(size_t)c * NF + tid], itB = p.itB[(size_t)c * NF + tid];
+    const uint32_t itA = p.itA[(size_t)ct * NF + tid], itB = p.itB[(size_t)ct * NF + tid];
     const int l16 = tid & 15;
-    const uint32_t rmask = p.rowmask[c * 16 + l16];
+    const uint32_t rmask = p.rowmask[ct * 16 + l16];
     const int col = tid >> 4;
     float2* colp = ws + col * CS;
     __syncthreads();
@@ -296,13 +298,15 @@ int launch_mode(qmri_ctx* ctx, const K1Params& p, int S) {
         QCUDA(cudaFuncSetAttribute(stream_adj_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa));
         conf_a = sa;
     }
-    if (MODE != K1_ADJOINT) {
+    if (MODE != K1_ADJOINT && !(p.stage & K1_STAGE_ADJ_ONLY)) {
         stream_fwd_kernel<MODE><<<dim3(p.G, p.C, S), THREADS, sf, ctx->stream>>>(p);
         QLAUNCH_CHECK(ctx);
-        stream_solve_kernel<MODE><<<dim3(p.C, S), 256, 0, ctx->stream>>>(p);
-        QLAUNCH_CHECK(ctx);
+        if (!p.shared_mask) {
+            stream_solve_kernel<MODE><<<dim3(p.C, S), 256, 0, ctx->stream>>>(p);
+            QLAUNCH_CHECK(ctx);
+        }
     }
-    if (MODE != K1_FORWARD) {
+    if (MODE != K1_FORWARD && !(p.stage & K1_STAGE_FWD_ONLY)) {
         stream_adj_kernel<MODE><<<dim3(p.G, p.C, S), THREADS, sa, ctx->stream>>>(p);
         QLAUNCH_CHECK(ctx);
     }
@@ -331,7 +335,7 @@ int k1_stream_launch(qmri_ctx* ctx, const K1Params& p_in, int S, int ns_max) {
     p.ns_max = ns_max;
     if (p.G < 1 || SLABS % p.G || !p.part || !p.cbuf) return qmri_fail(QMRI_EINVAL, "x-update (streaming kernel): bad slab grouping / scratch");
     p.slabs_per_cta = SLABS / p.G;
-    if (adj_smem(p) > 56 * 1024) return qmri_fail(QMRI_EUNSUPPORTED, "x-update (streaming kernel): %zu bytes of shared memory needed", adj_smem(p));
+    if (adj_smem(p) > 100 * 1024) return qmri_fail(QMRI_EUNSUPPORTED, "x-update (streaming kernel): %zu bytes of shared memory needed", adj_smem(p));
     switch (p.mode) {
         case K1_ADMM: return launch_mode<K1_ADMM>(ctx, p, S);
         case K1_SOLVE: return launch_mode<K1_SOLVE>(ctx, p, S);

@@ -544,11 +544,86 @@ def test_large_batch_takes_streaming_kernel_and_matches_oracle(q, ops):
     for s in (0, 7, 19, 31):
         assert rel_l2(y[:, s], yo * scale[s]) <= TOL_XUPDATE
 
+
+# ---------------------------------------------------------------------------------------------
+# general V: frame i samples sum_c V(i,c) X^_c on its own mask; exact block solve per k-space location
+def general_ops(q, kind, V):
+    from oracle import sampling
+    if kind == "spiral":
+        return q.setup_subsampling_spiralgrided(224, 224, 771, V), sampling.setup_subsampling_spiralgrided(224, 224, 771, V)
+    return q.setup_subsampling_epi(224, 224, 1 / 65, V), sampling.setup_subsampling_epi(224, 224, 1 / 65, V)
+
+
+def tsmi_c(seed, C, S=None, cplx=False):
+    x = smooth_tsmi(seed, S=S, cplx=cplx)
+    return x[:, :, :C] if S is None else x[:, :, :C, :]
+
+
+@pytest.mark.parametrize("kind,L,C", [("spiral", 12, 10), ("spiral", 6, 4), ("epi", 5, 4)])
+def test_general_V_operator_and_xupdate(q, kind, L, C):
+    from oracle.sampling import FOperator
+    from oracle.xupdate import xupdate_exact
+    rng = np.random.default_rng(60 + L)
+    V = rng.standard_normal((L, C)) / np.sqrt(C)
+    P, Po = general_ops(q, kind, V)
+    F, Fo = q.fft_operator(P), FOperator(Po)
+    assert P.nmeas == Po.nmeas
+    x = tsmi_c(61, C, S=2, cplx=True)
+    y = F.forward(x)
+    for s in range(2):
+        assert rel_l2(y[:, s], Fo.forward(x[..., s])) <= TOL_XUPDATE
+    b = rng.standard_normal((P.nmeas, 2)) + 1j * rng.standard_normal((P.nmeas, 2))
+    xa = F.adjoint(b)
+    for s in range(2):
+        assert rel_l2(xa[..., s], Fo.adjoint(b[:, s])) <= TOL_XUPDATE
+    lhs, rhs = np.vdot(b, y), np.vdot(xa, x)             # <A x, b> == <x, A^H b>
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    yv = Fo.forward(tsmi_c(62, C))
+    v, u = tsmi_c(63, C), 0.1 * tsmi_c(64, C, cplx=True)
+    for rho in (0.05, 0.7):
+        xs, w, mm = F.xupdate(yv, v, u, rho, want_w=True)
+        xo = xupdate_exact(Fo, yv, v - u, rho)
+        assert rel_l2(xs, xo) <= TOL_XUPDATE
+        assert rel_l2(w, xo + u) <= TOL_XUPDATE
+
+
+def test_general_V_admm_loop(q):
+    from oracle.admm import pnp_admm
+    from oracle.sampling import FOperator
+    from oracle.synth import awgn_measured
+    rng = np.random.default_rng(70)
+    V = np.linalg.qr(rng.standard_normal((12, 10)))[0] * 1.3      # 12 frames, 10 channels, A A^H != I
+    P, Po = general_ops(q, "spiral", V)
+    Fo = FOperator(Po)
+    Xgt = smooth_tsmi(71, S=2)
+    Y = np.stack([awgn_measured(Fo.forward(Xgt[..., s]), 30, 71 + s) for s in range(2)], axis=1)
+    X0 = Fo.adjoint(Y)
+    param = {"iter": 5, "gamma": 0.05, "denoiser_type": "single_level"}
+    x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=box_denoiser, X0=X0))
+    for s in range(2):
+        xo = pnp_admm(Y[:, s], dict(param, F=Fo, net=box_denoiser, X0=X0[..., s]), solver="exact")
+        assert rel_l2(x[..., s], xo) <= TOL_XUPDATE
+
+
+def test_admm_honours_any_X0(q, ops):
+    """param.X0 is the caller's: iteration 1 solves from it (PnP_ADMM.m:76-78,102), whether or not it equals A^H y."""
+    from oracle.admm import pnp_admm
+    P, Po = ops["spiral"]
+    Fo, Xgt, Y, X0 = make_problem(Po, 72)
+    X0b = 0.5 * X0 + 0.1 * smooth_tsmi(73, cplx=True)
+    for it in (1, 3):
+        param = {"iter": it, "gamma": 0.05, "denoiser_type": "single_level"}
+        xo = pnp_admm(Y, dict(param, F=Fo, net=box_denoiser, X0=X0b), solver="exact")
+        x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=box_denoiser, X0=X0b))
+        assert rel_l2(x, xo) <= TOL_XUPDATE
+
 # ---------------------------------------------------------------------------------------------
 def test_error_behaviour(q):
     V = np.eye(10)
     with pytest.raises(q.QmriError):
-        q.setup_subsampling_spiralgrided(224, 224, 771, np.ones((10, 10)))       # unsupported V
+        q.setup_subsampling_spiralgrided(224, 224, 771, np.ones((200, 10)))      # union of 200 masks (11 051 locations): beyond this build's limit
+    with pytest.raises(q.QmriError):
+        q.setup_subsampling_spiralgrided(224, 224, 771, np.ones((12, 20)))       # general V: at most 16 channels
     with pytest.raises(q.QmriError):
         q.setup_subsampling_spiralgrided(128, 128, 771, V)                       # unsupported size
     with pytest.raises(q.QmriError):
