@@ -5,6 +5,7 @@
 // nor called by, libqmri_b200.so.
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -297,7 +298,8 @@ int k1emu_run(int mode, int mc, int pattern, double arg, int C, int S, const flo
     if (pattern == 0) optab::spiral_frames(NF, (int)arg, C, frames);
     else optab::epi_frames(NF, NF, arg, C, frames);
     optab::K1Tables t;
-    optab::build_k1_tables(NF, frames, t);
+    const char* env = getenv("QMRI_K1_QMIN");  // same knob and default as the library (qmri_api.cu)
+    optab::build_k1_tables(NF, frames, t, env ? atoi(env) : 8);
     if (mc == 0) {  // streaming kernel
         if (!t.stream_ok) return -1;
         emulate_stream(mode, C, S, t, in_re, in_im, v, y, rho, out_re, out_im, y_out, minmax);

@@ -617,6 +617,49 @@ def test_admm_honours_any_X0(q, ops):
         x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=box_denoiser, X0=X0b))
         assert rel_l2(x, xo) <= TOL_XUPDATE
 
+
+# ---------------------------------------------------------------------------------------------
+# full size (BASELINE configs[3]: 120 slices): size-independent properties
+def test_full_size_120_slices_recon_and_matching(q, ops):
+    """120-slice PnP-ADMM batch with the built-in UNetRes + matching of every pixel.  Slices are independent, so (a) a slice of the
+    batch equals the same slice reconstructed alone, (b) a permuted batch gives the permuted result (to the denoiser tolerance: kernel shapes follow the chunk), (c) two slices
+    against the oracle loop, (d) matched indices of the whole batch equal those of the same slices matched alone."""
+    from oracle import synth, unetres
+    from oracle.admm import pnp_admm
+    import bench
+    P, Po = ops["spiral"]
+    F = q.fft_operator(P)
+    S = 120
+    X = bench.synthetic_slices(S, seed=77)
+    Y = F.forward(X)
+    rng = np.random.default_rng(78)
+    Y = Y + (rng.standard_normal(Y.shape) + 1j * rng.standard_normal(Y.shape)) * np.sqrt(np.mean(np.abs(Y) ** 2) / 10 ** 3.0 / 2)
+    X0 = F.adjoint(Y)
+    sd = unetres.make_state_dict(10, seed=0)
+    net = q.UNetRes(sd, in_nc=10)
+    param = {"iter": 6, "gamma": 0.05, "denoiser_type": "single_level", "F": F, "net": net}
+    x = q.PnP_ADMM(Y, dict(param, X0=X0))
+    assert x.shape == (224, 224, 10, S) and np.isfinite(x).all()
+    pick = [0, 59, 119]
+    for s in pick:                                                     # (a)
+        xs = q.PnP_ADMM(Y[:, s], dict(param, X0=X0[..., s]))
+        assert rel_l2(x[..., s], xs) <= TOL_DENOISER                   # tile / split-K / x-update kernel choices depend on the batch size: not bitwise
+    perm = rng.permutation(S)                                          # (b)
+    xp = q.PnP_ADMM(np.ascontiguousarray(Y[:, perm]), dict(param, X0=np.ascontiguousarray(X0[..., perm])))
+    assert rel_l2(xp, x[..., perm]) <= TOL_DENOISER       # the last denoiser chunk (120 = 7 x 16 + 8) picks other tile shapes: not bitwise
+    assert np.isfinite(xp).all()
+    from oracle.sampling import FOperator                              # (c)
+    Fo = FOperator(Po)
+    for s in pick[:2]:
+        xo = pnp_admm(Y[:, s], dict(param, F=Fo, net=lambda v: unetres.denoise_matlab_layout(sd, v), X0=X0[..., s]), solver="exact")
+        assert rel_l2(x[..., s], xo) <= 1e-4
+    d = synth.make_dictionary(K_target=20000, cut=3, seed=0)          # (d)
+    out = q.mrf_dtm_cpu(d, {"X": np.transpose(x, (0, 1, 3, 2))}, {"f": {"qout": 1, "pdout": 1, "dmout": 1}})   # [Nx, Ny, Nz, T]
+    assert out["dm"].shape == (224, 224, S) and out["qmap"].shape == (224, 224, S, 2)
+    for s in pick:
+        o1 = q.mrf_dtm_cpu(d, {"X": x[..., s]}, {"f": {"qout": 1, "pdout": 1, "dmout": 1}})
+        assert np.array_equal(o1["dm"], out["dm"][:, :, s]) and np.array_equal(o1["qmap"], out["qmap"][:, :, s, :])
+
 # ---------------------------------------------------------------------------------------------
 def test_error_behaviour(q):
     V = np.eye(10)
