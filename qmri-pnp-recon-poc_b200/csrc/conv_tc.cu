@@ -125,6 +125,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
+// Programmatic dependent launch: the next conv kernel of the stream may be scheduled - and run its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) on SMs that are free - while this one is still running; it must not touch memory written by its
+// predecessors before pdl_wait() returns (= every earlier kernel has completed and flushed).  QMRI_NO_PDL=1 launches without it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -388,10 +393,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // everything below reads activations / partials / tickets produced by earlier kernels
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -674,6 +681,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
     }
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) TC_TRACE(7, -1);
@@ -681,6 +689,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     if (threadIdx.x == 0) TC_TRACE(7, -2);
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // everything below reads activations / partials / tickets produced by earlier kernels
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
@@ -983,6 +992,11 @@ int tc_block_n(int Cout) { return Cout == 64 ? 64 : 128; }
 size_t tc_partial_elems(int sm_count) { return (size_t)sm_count * TC_BM * 256; }
 size_t tc_ticket_count(int sm_count) { return (size_t)sm_count * 4; }
 
+static bool tc_pdl_enabled() {
+    static const bool on = getenv("QMRI_NO_PDL") == nullptr;
+    return on;
+}
+
 template <int BN, int MODE>
 static int launch_tc(qmri_ctx* ctx, const TcMaps& maps, const TcK& k, int grid) {
     static bool configured = false;
@@ -990,7 +1004,17 @@ static int launch_tc(qmri_ctx* ctx, const TcMaps& maps, const TcK& k, int grid) 
         QCUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM));
         configured = true;
     }
-    tc_conv_kernel<BN, MODE><<<grid, TC_THREADS, TcCfg<BN>::SMEM, ctx->stream>>>(maps, k);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcCfg<BN>::SMEM;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tc_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QCUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, MODE>, maps, k));
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
 }
@@ -1101,13 +1125,15 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = tc_pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     static int* trace_host = nullptr;
     static int* trace_dev = nullptr;
     static const bool trace_on = getenv("QMRI_TC_TRACE") != nullptr;
