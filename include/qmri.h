@@ -85,8 +85,8 @@ const char* qmri_last_error(void);
  * and the closures F.forward / F.adjoint of main_recon_tsmis_FFT.m:228-229.
  * V is L x C column-major, real (the reference passes real(dict.V)).
  * Scope of this build: N == M == 224.  V == eye(C) (the BASELINE configuration) takes the diagonal data-consistency
- * path; any other real L x C V (C <= 16) takes the exact per-location block solve, as long as the union of the L masks
- * holds at most 4096 k-space locations (about 15 spiral frames) - beyond that QMRI_EUNSUPPORTED.
+ * path; any other real L x C V (C <= 16) takes the exact per-location block solve on the union of the L masks
+ * (the union is processed in parts of <= 3400 k-space locations, e.g. 4 parts for 200 spiral frames).
  */
 int qmri_op_spiral(qmri_ctx* ctx, int N, int M, int S_curve, const double* V, int L, int C, qmri_op** out);
 int qmri_op_epi(qmri_ctx* ctx, int N, int M, double percentage, const double* V, int L, int C, qmri_op** out);

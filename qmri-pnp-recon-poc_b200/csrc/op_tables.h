@@ -254,6 +254,7 @@ static inline void build_k1_tables(int N, const std::vector<std::vector<int32_t>
 // P = vertical stack of S_i kron(conj(V(i,:)), I): frame i samples sum_c V(i,c) X^_c on its own mask Omega_i.  The normal matrix
 // is block diagonal in k-space: at location k the C x C block G_k = sum_{i: k in Omega_i} V(i,:)^T V(i,:).  All channels are
 // therefore transformed on the UNION of the masks (one shared work-item table), and small per-location kernels mix channels.
+constexpr int GENERAL_PART_MAX = 3400;   // union locations per part (shared memory: 12 bytes per location in the forward kernel)
 struct GeneralTables {
     int L = 0, C = 0, nU = 0;
     std::vector<int32_t> ulist;        // [nU] union of the sampled locations, ascending k = k1 + N k2
@@ -263,7 +264,12 @@ struct GeneralTables {
     std::vector<int32_t> meas_u;       // [nmeas] union slot of measurement j
     std::vector<int32_t> meas_frame;   // [nmeas] frame of measurement j
     std::vector<float> V;              // [L][C] row-major
-    K1Tables tu;                       // streaming-kernel tables of the single pseudo-frame "union"
+    // The union is cut into contiguous parts (bands of k2) small enough for the streaming kernels' work-item tables and shared
+    // memory; part p covers union slots [part_off[p], part_off[p+1]).  The transforms are linear in the mask, so the forward
+    // kernel runs once per part and the adjoint passes accumulate.
+    std::vector<K1Tables> parts;
+    std::vector<int32_t> part_off;     // [P + 1]
+    bool ok = false;
 };
 
 static inline void build_general_tables(int N, const std::vector<std::vector<int32_t>>& frames, const double* Vcm /*L x C col-major*/,
@@ -305,8 +311,22 @@ static inline void build_general_tables(int N, const std::vector<std::vector<int
         }
         g.memb_ptr[u + 1] = (int32_t)g.memb_frame.size();
     }
-    std::vector<std::vector<int32_t>> one(1, g.ulist);
-    build_k1_tables(N, one, g.tu, stream_q_min);
+    // parts: as few as possible, each within the streaming kernels' limits
+    g.ok = false;
+    for (int P = std::max(1, (g.nU + GENERAL_PART_MAX - 1) / GENERAL_PART_MAX); P <= 32 && !g.ok; ++P) {
+        g.parts.assign(P, K1Tables());
+        g.part_off.assign(P + 1, 0);
+        bool all = true;
+        for (int pi = 0; pi < P; ++pi) {
+            const int a = (int)((int64_t)g.nU * pi / P), b = (int)((int64_t)g.nU * (pi + 1) / P);
+            g.part_off[pi] = a;
+            g.part_off[pi + 1] = b;
+            std::vector<std::vector<int32_t>> one(1, std::vector<int32_t>(g.ulist.begin() + a, g.ulist.begin() + b));
+            build_k1_tables(N, one, g.parts[pi], stream_q_min);
+            all = all && g.parts[pi].stream_ok;
+        }
+        g.ok = all;
+    }
 }
 
 // (G_u + rho I)^{-1} for every union location, row-major C x C, computed in double (Gauss-Jordan with partial pivoting on an SPD matrix)

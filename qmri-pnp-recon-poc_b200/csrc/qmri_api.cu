@@ -225,6 +225,40 @@ extern "C" int64_t qmri_ctx_launch_count(qmri_ctx* ctx) { return ctx ? ctx->laun
 // ------------------------------------------------------------------------------------------
 // acquisition operator
 // ------------------------------------------------------------------------------------------
+// device copy of one set of streaming-kernel tables (general V: one per part of the union mask)
+struct StreamDev {
+    float2 *tw2 = nullptr, *tw448 = nullptr;
+    uint32_t *itA = nullptr, *itB = nullptr, *ent = nullptr;
+    uint16_t* rowmask = nullptr;
+    int* frame_ptr = nullptr;
+    int ns_max = 0, n_ovf = 0;
+    int upload(const optab::K1Tables& t) {
+        int r = 0;
+        r |= dev_alloc(&tw2, (size_t)256);
+        r |= dev_alloc(&tw448, t.tw448.size() / 2);
+        r |= dev_alloc(&itA, t.itA.size());
+        r |= dev_alloc(&itB, t.itB.size());
+        r |= dev_alloc(&ent, t.ent.size());
+        r |= dev_alloc(&rowmask, t.rowmask.size());
+        r |= dev_alloc(&frame_ptr, t.frame_ptr.size());
+        if (r) return QMRI_ENOMEM;
+        cudaMemcpy(tw2, t.tw2.data(), sizeof(float) * t.tw2.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(tw448, t.tw448.data(), sizeof(float) * t.tw448.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(itA, t.itA.data(), sizeof(uint32_t) * t.itA.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(itB, t.itB.data(), sizeof(uint32_t) * t.itB.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(ent, t.ent.data(), sizeof(uint32_t) * t.ent.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(rowmask, t.rowmask.data(), sizeof(uint16_t) * t.rowmask.size(), cudaMemcpyHostToDevice);
+        cudaError_t e = cudaMemcpy(frame_ptr, t.frame_ptr.data(), sizeof(int) * t.frame_ptr.size(), cudaMemcpyHostToDevice);
+        ns_max = t.ns_max;
+        n_ovf = t.n_ovf;
+        return e == cudaSuccess ? QMRI_OK : qmri_fail(QMRI_ECUDA, "operator table upload failed: %s", cudaGetErrorString(e));
+    }
+    void release() {
+        cudaFree(tw2); cudaFree(tw448); cudaFree(itA); cudaFree(itB); cudaFree(ent); cudaFree(rowmask); cudaFree(frame_ptr);
+        tw2 = tw448 = nullptr; itA = itB = ent = nullptr; rowmask = nullptr; frame_ptr = nullptr;
+    }
+};
+
 struct qmri_op {
     qmri_ctx* ctx = nullptr;
     int N = 0, M = 0, C = 0, L = 0;
@@ -245,11 +279,11 @@ struct qmri_op {
     // general V (not the identity): channels are transformed on the union of the masks and mixed per k-space location
     bool general = false;
     optab::GeneralTables g;
+    std::vector<StreamDev> gparts;
     float* d_V = nullptr;
     int *d_memb_ptr = nullptr, *d_memb_frame = nullptr, *d_memb_meas = nullptr, *d_meas_u = nullptr, *d_meas_frame = nullptr;
     float* d_minv = nullptr;      // [nU][C][C] (G_u + rho I)^{-1} for minv_rho
     double minv_rho = -1.0;
-    const optab::K1Tables& stream_tables() const { return general ? g.tu : t; }
     // scratch for the host entry points
     DevBuf stage, a_re, a_im, b_re, b_im, c_re, c_im, ybuf, mm_ord, mm_f;
     DevBuf k1_part, k1_cbuf;  // streaming x-update: partial sample sums / solved samples
@@ -296,14 +330,14 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     op->general = !identity;
     if (op->general) {
         optab::build_general_tables(N, frames, V, L, C, op->g, q_min);
-        if (!op->g.tu.stream_ok || op->g.nU > 4096) {
+        if (!op->g.ok) {
             const int nU = op->g.nU;
             delete op;
-            return qmri_fail(QMRI_EUNSUPPORTED, "general V: the union of the %d masks holds %d k-space locations; this build handles up to 4096 "
-                             "(about 15 spiral frames) - SURVEY.md 8f-2", L, nU);
+            return qmri_fail(QMRI_EUNSUPPORTED, "general V: the union of the %d masks (%d k-space locations) does not fit the streaming "
+                             "kernels' work-item tables even in 32 parts - SURVEY.md 8f-2", L, nU);
         }
     }
-    const optab::K1Tables& t = op->stream_tables();  // device tables: per-frame masks (V = I) or the union mask (general V)
+    const optab::K1Tables& t = op->t;
     size_t nm = std::max(1, t.nmeas);
     int r = 0;
     r |= dev_alloc(&op->d_tw, (size_t)N);
@@ -326,6 +360,8 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
         r |= dev_alloc(&op->d_meas_u, nmf);
         r |= dev_alloc(&op->d_meas_frame, nmf);
         r |= dev_alloc(&op->d_minv, std::max<size_t>((size_t)g.nU * C * C, 1));
+        op->gparts.resize(g.parts.size());
+        for (size_t pi = 0; pi < g.parts.size() && !r; ++pi) r |= op->gparts[pi].upload(g.parts[pi]);
         if (!r) {
             cudaMemcpy(op->d_V, g.V.data(), sizeof(float) * g.V.size(), cudaMemcpyHostToDevice);
             cudaMemcpy(op->d_memb_ptr, g.memb_ptr.data(), sizeof(int) * g.memb_ptr.size(), cudaMemcpyHostToDevice);
@@ -388,6 +424,7 @@ extern "C" int qmri_op_destroy(qmri_op* op) {
     cudaFree(op->d_p4tab);
     cudaFree(op->d_V); cudaFree(op->d_memb_ptr); cudaFree(op->d_memb_frame); cudaFree(op->d_memb_meas); cudaFree(op->d_meas_u);
     cudaFree(op->d_meas_frame); cudaFree(op->d_minv);
+    for (auto& sd : op->gparts) sd.release();
     cudaFree(op->d_tw2); cudaFree(op->d_tw448); cudaFree(op->d_itA); cudaFree(op->d_itB); cudaFree(op->d_ent); cudaFree(op->d_rowmask);
     op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
     op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
@@ -410,13 +447,15 @@ extern "C" int qmri_op_indices(const qmri_op* op, int32_t* idx, int64_t* frame_p
 // 7.4 us at eight, 6.97 vs 4.37 us per slice at 120.  QMRI_K1_KERNEL=cluster|stream forces one (tests, profiling).
 // part / cbuf: scratch of the streaming kernels.  The host entry points use the operator's; an ADMM session brings its own,
 // sized once for its batch, because its CUDA graph keeps the addresses.
-// General V: forward transform of every channel on the union mask -> per-location channel mixing -> adjoint transform.
+// General V: forward transform of every channel on the union mask (one launch per part of the union) -> per-location channel
+// mixing -> adjoint transform (the parts' corrections accumulate: the first pass runs the caller's mode, the others add in place).
 static int k1_general_dispatch(qmri_op* op, K1Params p, int S, DevBuf* part, DevBuf* cbuf) {
     qmri_ctx* ctx = op->ctx;
     const optab::GeneralTables& g = op->g;
-    const int nU = g.nU;
+    const int nU = g.nU, P = (int)g.parts.size();
     p.shared_mask = 1;
     p.G = k1_stream_groups(S, op->C, ctx->sm_count);
+    p.slot_stride = nU;
     QCHECK(part->ensure(std::max<size_t>(k1_stream_part_elems(S, op->C, p.G, nU), 1) * sizeof(float2)));
     QCHECK(cbuf->ensure(std::max<size_t>(k1_stream_cbuf_elems(S, op->C, nU), 1) * sizeof(float2)));
     p.part = part->as<float2>();
@@ -427,14 +466,52 @@ static int k1_general_dispatch(qmri_op* op, K1Params p, int S, DevBuf* part, Dev
     m.memb_ptr = op->d_memb_ptr; m.memb_frame = op->d_memb_frame; m.memb_meas = op->d_memb_meas;
     m.meas_u = op->d_meas_u; m.meas_frame = op->d_meas_frame;
     m.S = S; m.C = op->C; m.L = op->L; m.G = p.G; m.nU = nU; m.nmeas = op->t.nmeas;
+    auto use_part = [&](K1Params& q, int pi) {
+        const StreamDev& sd = op->gparts[pi];
+        q.tw2 = sd.tw2; q.tw448 = sd.tw448; q.itA = sd.itA; q.itB = sd.itB; q.ent = sd.ent; q.rowmask = sd.rowmask;
+        q.frame_ptr = sd.frame_ptr; q.n_ovf = sd.n_ovf;
+        q.slot_off = g.part_off[pi];
+        return sd.ns_max;
+    };
+    auto forward_all = [&]() -> int {
+        K1Params q = p;
+        q.stage = K1_STAGE_FWD_ONLY;
+        for (int pi = 0; pi < P; ++pi) {
+            const int ns = use_part(q, pi);
+            QCHECK(k1_stream_launch(ctx, q, S, ns));
+        }
+        return QMRI_OK;
+    };
+    // pass 0 writes `mode`'s result, passes 1.. add their part of the correction in place (SOLVE mode: out = in + corr)
+    auto adjoint_all = [&]() -> int {
+        for (int pi = 0; pi < P; ++pi) {
+            K1Params q = p;
+            q.stage = K1_STAGE_ADJ_ONLY;
+            const int ns = use_part(q, pi);
+            const bool last = pi == P - 1;
+            if (pi > 0) {
+                q.mode = K1_SOLVE;
+                q.in_re = p.out_re; q.in_im = p.out_im;
+                q.x_re = q.x_im = nullptr;
+            }
+            if (!last) q.minmax = nullptr;  // min / max of the finished image only
+            QCHECK(k1_stream_launch(ctx, q, S, ns));
+            if (pi > 0 && p.mode == K1_ADMM && p.x_re) {  // last iteration: x receives the same corrections
+                K1Params qx = q;
+                qx.in_re = p.x_re; qx.in_im = p.x_im; qx.out_re = p.x_re; qx.out_im = p.x_im;
+                qx.minmax = nullptr;
+                QCHECK(k1_stream_launch(ctx, qx, S, ns));
+            }
+        }
+        return QMRI_OK;
+    };
     if (p.mode == K1_FORWARD) {
-        p.stage = K1_STAGE_FWD_ONLY;
-        QCHECK(k1_stream_launch(ctx, p, S, nU));
+        QCHECK(forward_all());
         return k1_general_mix_forward(ctx, m);
     }
     if (p.mode == K1_ADJOINT) {
         QCHECK(k1_general_mix_adjoint(ctx, m));
-        return k1_stream_launch(ctx, p, S, nU);
+        return adjoint_all();
     }
     if (!(p.rho > 0.0)) return qmri_fail(QMRI_EINVAL, "x-update: rho must be positive");
     if (op->minv_rho != p.rho) {  // happens on the first x-update of a run, i.e. before any CUDA-graph capture of the loop
@@ -444,11 +521,9 @@ static int k1_general_dispatch(qmri_op* op, K1Params p, int S, DevBuf* part, Dev
         QCUDA(cudaMemcpy(op->d_minv, minv.data(), sizeof(float) * minv.size(), cudaMemcpyHostToDevice));
         op->minv_rho = p.rho;
     }
-    p.stage = K1_STAGE_FWD_ONLY;
-    QCHECK(k1_stream_launch(ctx, p, S, nU));
+    QCHECK(forward_all());
     QCHECK(k1_general_mix_solve(ctx, m));
-    p.stage = K1_STAGE_ADJ_ONLY;
-    return k1_stream_launch(ctx, p, S, nU);
+    return adjoint_all();
 }
 
 static int k1_dispatch(qmri_op* op, const K1Params& p_in, int S, DevBuf* part = nullptr, DevBuf* cbuf = nullptr) {
@@ -489,7 +564,7 @@ static void k1_fill_tables(const qmri_op* op, K1Params& p) {
     p.itB = op->d_itB;
     p.ent = op->d_ent;
     p.rowmask = op->d_rowmask;
-    p.n_ovf = op->stream_tables().n_ovf;
+    p.n_ovf = op->t.n_ovf;
     p.C = op->C;
     p.nmeas = op->t.nmeas;
 }

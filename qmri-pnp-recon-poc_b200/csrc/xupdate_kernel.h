@@ -38,6 +38,8 @@ struct K1Params {
     int n_ovf;               // overflow partials per frame (sizes the shared-memory slots)
     float2* part;            // scratch [S][C][G][ns_max] partial sample sums of the forward kernel
     float2* cbuf;            // scratch [S][C][ns_max]    c = (y - A z) / (1 + rho)
+    int slot_off;            // general V: first union slot of the part these tables cover (0 otherwise)
+    int slot_stride;         // samples per image in part / cbuf (general V: the whole union; otherwise ns_max; set by k1_stream_launch)
     int stage;               // general V: K1_STAGE_FWD_ONLY / K1_STAGE_ADJ_ONLY run one half of the streaming path (0 = both)
     int shared_mask;         // general V: every channel is transformed on the same (union) mask - tables of "frame" 0, cbuf in all modes
     int G;                   // slab groups (CTAs) per image: 2, 4, 8 or 16

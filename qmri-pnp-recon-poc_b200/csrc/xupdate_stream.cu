@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, 4) stream_fwd_kernel(K1Params p) {
         __syncthreads();
     }
     // every sample belongs to exactly one work item, i.e. to one thread: no race on pc above
-    float2* part = p.part + (((size_t)s * p.C + c) * p.G + g) * (size_t)p.ns_max;
+    float2* part = p.part + (((size_t)s * p.C + c) * p.G + g) * (size_t)p.slot_stride + p.slot_off;
     for (int j = tid; j < ns; j += THREADS) part[j] = pc[j];
 }
 
@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(256) stream_solve_kernel(K1Params p) {
     const int f0 = p.frame_ptr[c];
     const int ns = p.frame_ptr[c + 1] - f0;
     const float inv_n = 1.0f / (float)NF;  // unitary scaling 1/sqrt(N*M), once per transform direction
-    const float2* part = p.part + ((size_t)s * p.C + c) * p.G * (size_t)p.ns_max;
+    const float2* part = p.part + ((size_t)s * p.C + c) * p.G * (size_t)p.slot_stride;
     for (int j = threadIdx.x; j < ns; j += blockDim.x) {
         float sx = 0.f, sy = 0.f;
         for (int g = 0; g < p.G; ++g) {  // fixed order: deterministic
-            const float2 t = part[(size_t)g * p.ns_max + j];
+            const float2 t = part[(size_t)g * p.slot_stride + j];
             sx += t.x;
             sy += t.y;
         }
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) stream_solve_kernel(K1Params p) {
         } else {
             const float2 y = p.y[yi];
             const float gsc = p.inv_1p_rho * inv_n;  // (y - A z)/(1 + rho), pre-scaled for the inverse transform
-            p.cbuf[((size_t)s * p.C + c) * p.ns_max + j] = make_float2((y.x - sx) * gsc, (y.y - sy) * gsc);
+            p.cbuf[((size_t)s * p.C + c) * p.slot_stride + j] = make_float2((y.x - sx) * gsc, (y.y - sy) * gsc);
         }
     }
 }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(THREADS, 4) stream_adj_kernel(K1Params p) {
             const float2 y = p.y[(size_t)s * p.nmeas + f0 + i];
             pc[i] = make_float2(y.x * (1.0f / (float)NF), y.y * (1.0f / (float)NF));
         } else {
-            pc[i] = p.cbuf[((size_t)s * p.C + c) * p.ns_max + i];
+            pc[i] = p.cbuf[((size_t)s * p.C + c) * p.slot_stride + p.slot_off + i];
         }
     }
     const uint32_t itA = p.itA[(size_t)ct * NF + tid], itB = p.itB[(size_t)ct * NF + tid];
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(THREADS, 4) stream_adj_kernel(K1Params p) {
             } else if (MODE == K1_SOLVE) {
 #pragma unroll
                 for (int d = 0; d < 14; ++d) {
-                    br[d] = __ldg(p.in_re + gl + 16 * d);
-                    bi[d] = p.in_im ? __ldg(p.in_im + gl + 16 * d) : 0.f;
+                    br[d] = p.in_re[gl + 16 * d];  // plain loads: the general-V accumulation passes run this mode in place (in == out)
+                    bi[d] = p.in_im ? p.in_im[gl + 16 * d] : 0.f;
                 }
             }
             if (MODE == K1_ADMM && p.x_re) {  // last iteration: x = z + corr = 2 v - w + corr; w' may overwrite w in place, so x goes first
@@ -335,6 +335,10 @@ int k1_stream_launch(qmri_ctx* ctx, const K1Params& p_in, int S, int ns_max) {
     p.ns_max = ns_max;
     if (p.G < 1 || SLABS % p.G || !p.part || !p.cbuf) return qmri_fail(QMRI_EINVAL, "x-update (streaming kernel): bad slab grouping / scratch");
     p.slabs_per_cta = SLABS / p.G;
+    if (!p.shared_mask) {
+        p.slot_off = 0;
+        p.slot_stride = ns_max;
+    }
     if (adj_smem(p) > 100 * 1024) return qmri_fail(QMRI_EUNSUPPORTED, "x-update (streaming kernel): %zu bytes of shared memory needed", adj_smem(p));
     switch (p.mode) {
         case K1_ADMM: return launch_mode<K1_ADMM>(ctx, p, S);
