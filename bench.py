@@ -13,8 +13,11 @@ iterations: fused x-update kernel + 64-conv denoiser each).  N > 1: every rank r
   value : slice-iterations/s with y, X0 already resident in HBM (qmri_admm_run only), device-timed
   e2e   : the same through the reference-facing call PnP_ADMM(y, param) with HOST buffers: H2D of y and X0 and
           D2H of x inside the timed region
-  roofline       : dominant kernel = the denoiser's conv kernels (tensor-pipe bound), timed live
-  roofline_k1/k2 : the x-update kernel (HBM bound) and dictionary matching (fp32 pipe), timed live
+  roofline       : dominant kernel = the denoiser's conv kernels (tensor-pipe bound), timed live at the workload's slice count;
+                   `traffic` = DRAM bytes per forward from the committed ncu capture (profiles/traffic.json)
+  roofline_fwd_S15 : the same forward at 15 slices per GPU (machine filled), timed live
+  roofline_k1/k2 : the x-update kernels (HBM bound, 120 slices) and dictionary matching (fp32 pipe), timed live
+  clocks         : NVML samples taken during a second, identical timed pass (its time is reported too)
   cpu_baseline   : the oracle loop (NumPy x-update + PyTorch-CPU UNetRes) on the host cores, bounded sample
 
 `--impl reference` times that CPU implementation as the reference arm (no MATLAB/Octave exists here; the
@@ -311,6 +314,23 @@ def run_ours(args, rank, world, local_rank):
                 "traffic_note": (t_fwd or {}).get("how", "no committed ncu capture for this slice count"),
                 "peak_source": f"{peaks['src']} dense bf16 (sustained); the fp32 exact mode runs on CUDA cores, see DESIGN.md",
                 "ms_per_forward": ms_fwd / 5, "precision_mode": args.precision}
+    # the same forward with the machine filled (15 slices = BASELINE configs[2]'s per-GPU batch): what the conv kernels reach when
+    # a layer has enough tiles for 148 SMs - the single-slice figure above is bound by per-layer latency (64 dependent layers)
+    roof_fwd15 = None
+    if rank == 0 and world == 1 and not args.skip_extra and S != 15:
+        S15 = 15
+        vin15 = torch.rand(S15 * 10 * hw, device="cuda")
+        vout15 = torch.empty_like(vin15)
+        def fwd15():
+            q._capi.check(ctx.lib.qmri_unetres_forward_dev(net.handle, C.c_void_p(vin15.data_ptr()), C.c_void_p(vout15.data_ptr()), None, None, S15, N_IMG, N_IMG))
+        ms15, _ = timed(fwd15, 5, 3, collective=False)
+        tf15 = net.flops(S15, N_IMG, N_IMG) * 5 / (ms15 * 1e-3) / 1e12
+        t15 = traffic.get("unetres_forward_S15")
+        roof_fwd15 = {"bound": "tensor", "kernel": "UNetRes forward, 15 slices", "achieved": tf15, "peak": tensor_peak, "unit": "TFLOP/s",
+                      "frac": tf15 / tensor_peak, "frac_of_3_product_ceiling": 3 * tf15 / tensor_peak,
+                      "traffic": (t15["dram_read_bytes"] + t15["dram_write_bytes"]) if t15 else None, "ms_per_forward": ms15 / 5,
+                      "note": "split-bf16 operands need 3 bf16 products per fp32 product (1e-4 parity bar): ceiling = peak / 3"}
+        del vin15, vout15
     # K1 at a batch larger than L2 (algorithmic bytes: 20 B per pixel-channel per iteration)
     roof_k1 = None
     if rank == 0 and world == 1 and not args.skip_extra:  # single-GPU run only: the scaling runs stay short
@@ -377,6 +397,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_fwd_S15": roof_fwd15,
             "roofline_k1": roof_k1,
             "roofline_k2": roof_k2,
             "cpu_baseline": cpu,
