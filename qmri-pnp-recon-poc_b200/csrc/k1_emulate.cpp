@@ -309,4 +309,31 @@ int k1emu_run(int mode, int mc, int pattern, double arg, int C, int S, const flo
     else emulate<28>(mode, C, S, t, in_re, in_im, v, y, rho, out_re, out_im, y_out, minmax);
     return t.nmeas;
 }
+
+// General V host logic (op_tables.h): union / membership tables and the per-location inverses (G_u + rho I)^{-1}.
+// Returns nU; fills ulist [nU], nparts, and Minv [nU][C][C] when non-null.
+int k1emu_general(int pattern, double arg, int L, int C, const double* V, double rho, int32_t* ulist, int* nparts, float* Minv) {
+    std::vector<std::vector<int32_t>> frames;
+    if (pattern == 0) optab::spiral_frames(NF, (int)arg, L, frames);
+    else optab::epi_frames(NF, NF, arg, L, frames);
+    optab::GeneralTables g;
+    const char* env = getenv("QMRI_K1_QMIN");
+    optab::build_general_tables(NF, frames, V, L, C, g, env ? atoi(env) : 8);
+    if (!g.ok) return -1;
+    if (ulist) memcpy(ulist, g.ulist.data(), sizeof(int32_t) * g.nU);
+    if (nparts) *nparts = (int)g.parts.size();
+    if (Minv) {
+        std::vector<float> m;
+        optab::general_inverses(g, rho, m);
+        memcpy(Minv, m.data(), sizeof(float) * m.size());
+    }
+    // every measurement must be reachable from its union slot and the parts must tile the union
+    int64_t covered = 0;
+    for (size_t p = 0; p < g.parts.size(); ++p) covered += g.parts[p].nmeas;
+    if (covered != g.nU || (int)g.memb_meas.size() != (int)g.meas_u.size()) return -2;
+    for (int u = 0; u < g.nU; ++u)
+        for (int e = g.memb_ptr[u]; e < g.memb_ptr[u + 1]; ++e)
+            if (g.meas_u[g.memb_meas[e]] != u || g.meas_frame[g.memb_meas[e]] != g.memb_frame[e]) return -3;
+    return g.nU;
+}
 }

@@ -82,3 +82,29 @@ def test_k1_arithmetic_all_modes(emu, pat, arg, mc, monkeypatch):
     emu.k1emu_run(0, mc, pat, arg, C, 1, P(zr), P(zi), P(vr), P(y32), 0.05, P(ore), P(oim), None, P(mm))
     x = xupdate_exact(F, y, 2 * v - z, 0.05)
     assert rel_l2(unplanar(ore, oim), x + (z - v)) < 1e-6   # w' = x + u, u = w - v
+
+
+@pytest.mark.parametrize("pat,arg,L,C", [(0, 771.0, 12, 10), (0, 771.0, 200, 10), (1, 1 / 65, 5, 4)])
+def test_general_V_host_tables(emu, pat, arg, L, C):
+    """Union of the masks, membership lists, part tiling and (G_u + rho I)^-1 of the general-V path against NumPy."""
+    rng = np.random.default_rng(L)
+    V = np.asfortranarray(rng.standard_normal((L, C)))
+    Po = (sampling.setup_subsampling_spiralgrided(224, 224, 771, V) if pat == 0 else sampling.setup_subsampling_epi(224, 224, 1 / 65, V))
+    U = np.unique(np.concatenate([np.asarray(f) for f in Po.frames]))
+    emu.k1emu_general.restype = ctypes.c_int
+    emu.k1emu_general.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_double,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    ul = np.zeros(len(U), np.int32)
+    npart = ctypes.c_int(0)
+    Minv = np.zeros((len(U), C, C), np.float32)
+    rho = 0.05
+    n = emu.k1emu_general(pat, arg, L, C, V.ctypes.data, rho, ul.ctypes.data, ctypes.byref(npart), Minv.ctypes.data)
+    assert n == len(U) and np.array_equal(ul, U)
+    assert npart.value == -(-len(U) // 3400) or npart.value > len(U) // 3400
+    member = {int(k): [] for k in U}
+    for i, f in enumerate(Po.frames):
+        for k in f:
+            member[int(k)].append(i)
+    for u in rng.choice(len(U), size=40, replace=False):
+        G = sum(np.outer(V[i], V[i]) for i in member[int(U[u])])
+        assert np.allclose(Minv[u], np.linalg.inv(G + rho * np.eye(C)), rtol=2e-5, atol=1e-6)
