@@ -22,6 +22,7 @@
 // in the forward kernel, read v again (4 B) and write w' (8 B) in the adjoint kernel = 24 B against the
 // 20 B of the single-pass formulation; `part` and `c` add < 2 %.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "xupdate_kernel.h"
@@ -133,10 +134,16 @@ __global__ void __launch_bounds__(256) stream_solve_kernel(K1Params p) {
     const float2* part = p.part + ((size_t)s * p.C + c) * p.G * (size_t)p.slot_stride;
     for (int j = threadIdx.x; j < ns; j += blockDim.x) {
         float sx = 0.f, sy = 0.f;
-        for (int g = 0; g < p.G; ++g) {  // fixed order: deterministic
-            const float2 t = part[(size_t)g * p.slot_stride + j];
-            sx += t.x;
-            sy += t.y;
+#pragma unroll 1
+        for (int g0 = 0; g0 < p.G; g0 += 4) {  // fixed order: deterministic; four loads in flight (G is 4, 8 or 16; 2 only by hand)
+            float2 t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = g0 + i < p.G ? part[(size_t)(g0 + i) * p.slot_stride + j] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sx += t[i].x;
+                sy += t[i].y;
+            }
         }
         sx *= inv_n;
         sy *= inv_n;
@@ -315,14 +322,16 @@ int launch_mode(qmri_ctx* ctx, const K1Params& p, int S) {
 
 }  // namespace
 
-// Number of slab groups (CTAs) per image: the coarsest split whose last wave wastes <= 6 % (four CTAs per SM resident), else
-// the finest.  Coarser groups stage the operator tables less often; finer groups shorten the tail.
+// Number of slab groups (CTAs) per image: the coarsest split that still gives four waves of CTAs (four CTAs per SM resident), but
+// never coarser than 4.  Coarser groups stage the operator tables less often (13 KB per CTA against 37 KB of image data per
+// slab); measured on B200, us per slice-iteration: S = 120: G = 2 / 4 / 8 / 16 -> 4.20 / 4.13 / 4.34 / 4.92; S = 60: G = 4 / 8 ->
+// 4.50 / 4.58; S = 30: G = 8 / 16 -> 5.11 / 5.57.
 int k1_stream_groups(int S, int C, int sm_count) {
+    static const int forced = getenv("QMRI_K1_G") ? atoi(getenv("QMRI_K1_G")) : 0;  // tuning knob: 2, 4, 8 or 16
+    if (forced == 2 || forced == 4 || forced == 8 || forced == 16) return forced;
     const double slots = 4.0 * sm_count;
-    for (int G = 4; G <= SLABS; G *= 2) {
-        const double waves = (double)S * C * G / slots;
-        if (ceil(waves) / waves <= 1.06) return G;
-    }
+    for (int G = 4; G < SLABS; G *= 2)
+        if ((double)S * C * G / slots >= 4.0) return G;
     return SLABS;
 }
 size_t k1_stream_part_elems(int S, int C, int G, int ns_max) { return (size_t)S * C * G * ns_max; }
