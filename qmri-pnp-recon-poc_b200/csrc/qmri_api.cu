@@ -444,7 +444,7 @@ extern "C" int qmri_op_indices(const qmri_op* op, int32_t* idx, int64_t* frame_p
 // Kernel choice for one x-update launch: the streaming kernels (xupdate_stream.cu: forward / solve / adjoint, up to 16 CTAs
 // per slice-channel image) from about two slices on, the single cluster kernel (xupdate_kernel.cu: the image stays in the
 // shared memory of eight CTAs) below that - measured on B200: 23.8 vs 27.0 us at one slice, 16.2 vs 15.5 us at two, 9.1 vs
-// 7.4 us at eight, 6.97 vs 4.37 us per slice at 120.  QMRI_K1_KERNEL=cluster|stream forces one (tests, profiling).
+// 7.4 us at eight, 6.97 vs 4.13 us per slice at 120.  QMRI_K1_KERNEL=cluster|stream forces one (tests, profiling).
 // part / cbuf: scratch of the streaming kernels.  The host entry points use the operator's; an ADMM session brings its own,
 // sized once for its batch, because its CUDA graph keeps the addresses.
 // General V: forward transform of every channel on the union mask (one launch per part of the union) -> per-location channel
