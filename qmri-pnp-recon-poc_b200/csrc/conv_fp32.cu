@@ -250,9 +250,11 @@ __global__ void __launch_bounds__(256) resample_gemm_fp32_kernel(ConvParams p) {
 // CTA = 256 threads = a 32 x 8 pixel tile x 64 channels, 196 tiles per slice; the four cb lanes of a pixel group write the four
 // 32-byte quarters of the same 128-byte NHWC line.
 constexpr int HT_TW = 32, HT_PITCH = 36;   // tile width; patch row pitch in floats (34 used; 36 keeps rows 16-byte aligned)
-constexpr int HEAD_TH = 8, HEAD_ROWS = HEAD_TH + 2;
 constexpr int HEAD_WPITCH = 80;            // weights [9][Cin][4 cb][20]: 20-float blocks put the four cb lanes on different banks
-__global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
+// TH = tile height (8, or 4 for one or two slices: twice the CTAs for 148 SMs); CTA = 32 TH threads.
+template <int TH>
+__global__ void __launch_bounds__(32 * TH) head_fp32_kernel(HeadTailParams p) {
+    constexpr int HEAD_TH = TH, HEAD_ROWS = TH + 2, NT = 32 * TH;
     extern __shared__ __align__(16) float hsm[];
     const int Cin = p.Cin;
     float* patch = hsm;                                  // [Cin][10][36]
@@ -277,16 +279,16 @@ __global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
             if (c < Cpl) return (__ldg(p.planar_in + (((size_t)s * Cpl + c) * p.H + y) * p.W + x) - mn) * inv;
             return __ldg(p.noise_map + (size_t)y * p.W + x);
         };
-        for (int r0 = wrp; r0 < nrows; r0 += 32) {
+        for (int r0 = wrp; r0 < nrows; r0 += 4 * TH) {
             float v0[4], v1[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                v0[u] = fetch(r0 + 8 * u, lane);
-                v1[u] = lane < 2 ? fetch(r0 + 8 * u, 32 + lane) : 0.f;
+                v0[u] = fetch(r0 + TH * u, lane);
+                v1[u] = lane < 2 ? fetch(r0 + TH * u, 32 + lane) : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int r = r0 + 8 * u;
+                const int r = r0 + TH * u;
                 if (r < nrows) {
                     patch[r * HT_PITCH + lane] = v0[u];
                     if (lane < 4) patch[r * HT_PITCH + 32 + lane] = v1[u];  // columns 34, 35 are padding (zero)
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
             }
         }
     }
-    for (int t = tid; t < 9 * Cin * 16; t += 256) {  // float4 t = row (tap, c) x 16 quads
+    for (int t = tid; t < 9 * Cin * 16; t += NT) {  // float4 t = row (tap, c) x 16 quads
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w) + t);
         const int r = t >> 4, q16 = t & 15;
         *reinterpret_cast<float4*>(wts + r * HEAD_WPITCH + (q16 >> 2) * 20 + (q16 & 3) * 4) = w;
@@ -352,8 +354,10 @@ __global__ void __launch_bounds__(256) head_fp32_kernel(HeadTailParams p) {
 // deterministic), then lane kq stores pixel kq, so a warp writes 32 consecutive pixels of a plane.  CTA = 256 threads = a 32 x 8
 // pixel tile (196 per slice); K = 64 is staged in four chunks of 16 channels.  Patch planes are 10 x 36 floats: 360 = 8 mod 32
 // puts the four kq lanes on different banks.
-constexpr int TAIL_TH = 8, TAIL_ROWS = TAIL_TH + 2, TAIL_PLANE = TAIL_ROWS * HT_PITCH;
-__global__ void __launch_bounds__(256) tail_fp32_kernel(HeadTailParams p) {
+template <int TH>
+__global__ void __launch_bounds__(32 * TH) tail_fp32_kernel(HeadTailParams p) {
+    constexpr int TAIL_TH = TH, TAIL_ROWS = TH + 2, TAIL_PLANE = TAIL_ROWS * HT_PITCH, NT = 32 * TH;
+    static_assert(TAIL_PLANE % 32 == 8 || TAIL_PLANE % 32 == 24, "the four kq lanes must land on different banks");
     __shared__ __align__(16) float patch[16 * TAIL_PLANE];   // [16][10][36]
     __shared__ __align__(16) float wts[9 * 16 * 12];         // [9][16][12]
     const int tid = threadIdx.x;
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(256) tail_fp32_kernel(HeadTailParams p) {
 #pragma unroll 1
     for (int c0 = 0; c0 < 64; c0 += 16) {
         __syncthreads();
-        for (int t = tid; t < TAIL_ROWS * (HT_TW + 2) * 4; t += 256) {
+        for (int t = tid; t < TAIL_ROWS * (HT_TW + 2) * 4; t += NT) {
             int pix = t >> 2, q = t & 3;
             int py = pix / (HT_TW + 2), px = pix % (HT_TW + 2);
             int y = ty0 + py - 1, x = tx0 + px - 1;
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(256) tail_fp32_kernel(HeadTailParams p) {
             d[2 * TAIL_PLANE] = v.z;
             d[3 * TAIL_PLANE] = v.w;
         }
-        for (int t = tid; t < 9 * 16 * 12; t += 256) {
+        for (int t = tid; t < 9 * 16 * 12; t += NT) {
             int tap = t / 192, r = t % 192;
             int k = r / 12, co = r % 12;
             wts[t] = co < 10 ? __ldg(p.w + ((size_t)tap * 64 + c0 + k) * 10 + co) : 0.f;
@@ -471,25 +475,32 @@ int resample_fp32(qmri_ctx* ctx, const ConvParams& p) {
     return QMRI_OK;
 }
 
-int head_fp32(qmri_ctx* ctx, const HeadTailParams& p) {
-    size_t smem = (size_t)(p.Cin * HEAD_ROWS * HT_PITCH + 9 * p.Cin * HEAD_WPITCH) * sizeof(float);
+// tile height: 4 rows for one or two slices (392 CTAs per slice), 8 otherwise
+static inline int ht_tile_h(const HeadTailParams& p) { return p.S <= 2 ? 4 : 8; }
+
+template <int TH>
+static int head_launch(qmri_ctx* ctx, const HeadTailParams& p) {
+    size_t smem = (size_t)(p.Cin * (TH + 2) * HT_PITCH + 9 * p.Cin * HEAD_WPITCH) * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        QCUDA(cudaFuncSetAttribute(head_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QCUDA(cudaFuncSetAttribute(head_fp32_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid(((p.H + HEAD_TH - 1) / HEAD_TH) * ((p.W + HT_TW - 1) / HT_TW), 1, p.S);
-    head_fp32_kernel<<<grid, 256, smem, ctx->stream>>>(p);
+    dim3 grid(((p.H + TH - 1) / TH) * ((p.W + HT_TW - 1) / HT_TW), 1, p.S);
+    head_fp32_kernel<TH><<<grid, 32 * TH, smem, ctx->stream>>>(p);
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
 }
+int head_fp32(qmri_ctx* ctx, const HeadTailParams& p) { return ht_tile_h(p) == 4 ? head_launch<4>(ctx, p) : head_launch<8>(ctx, p); }
 
-int tail_fp32(qmri_ctx* ctx, const HeadTailParams& p) {
-    dim3 grid(((p.H + TAIL_TH - 1) / TAIL_TH) * ((p.W + HT_TW - 1) / HT_TW), 1, p.S);
-    tail_fp32_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+template <int TH>
+static int tail_launch(qmri_ctx* ctx, const HeadTailParams& p) {
+    dim3 grid(((p.H + TH - 1) / TH) * ((p.W + HT_TW - 1) / HT_TW), 1, p.S);
+    tail_fp32_kernel<TH><<<grid, 32 * TH, 0, ctx->stream>>>(p);
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
 }
+int tail_fp32(qmri_ctx* ctx, const HeadTailParams& p) { return ht_tile_h(p) == 4 ? tail_launch<4>(ctx, p) : tail_launch<8>(ctx, p); }
 
 int normalize_planar(qmri_ctx* ctx, const float* in, float* out, const float* minmax, size_t per_slice, int S, int undo) {
     dim3 grid((unsigned)((per_slice + 255) / 256), S);
