@@ -190,6 +190,7 @@ struct TcK {
     int S, H, W, Cin, Cout;
     int BW, BH, tiles_x, tiles_y;
     int relu, nsplit;
+    int cluster_splitk;  // split-K partials meet in the shared memory of a thread-block cluster of nsplit CTAs (one work item per CTA)
 };
 
 #define TC_TRACE(slot, val)                                                   \
@@ -351,6 +352,71 @@ __device__ __forceinline__ void tc_epilogue_reduce(const TcK& p, const float* pr
     }
 }
 
+// ---- split-K through distributed shared memory (cluster of nsplit CTAs = the K splits of one tile) ----------------------
+// Phase 1: this CTA's partial accumulator -> its own shared memory, column-major [BN][128] floats (lanes = rows: conflict-free).
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_park_smem(uint32_t taddr, float* red, int row, uint64_t* tfull_bar, uint32_t parity) {
+    mbar_wait(tfull_bar, parity);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[2][16];
+        tc_ld16(taddr + c0, acc[0]);
+        tc_ld16(taddr + c0 + 16, acc[1]);
+        tc_wait_ld();
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) red[(c0 + 16 * half + j) * TC_BM + row] = __uint_as_float(acc[half][j]);
+    }
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t mapa_rank_early(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// Phase 2 (after a cluster barrier): CTA `rank` finishes the 16-column chunks rank, rank + nsplit, ...: partials are added in
+// split order (the same order as the global-memory path: deterministic), then residuals / ReLU / split / store as usual.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_reduce_dsmem(const TcK& p, const float* red, int row, int rank, size_t o, bool ok) {
+    const uint32_t mine = smem_u32(red);
+#pragma unroll 1
+    for (int c0 = 16 * rank; c0 < BN; c0 += 16 * p.nsplit) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < p.nsplit; ++s) {
+            const uint32_t base = mapa_rank_early(mine, (uint32_t)s) + (uint32_t)((c0 * TC_BM + row) * 4);
+            float t[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) t[j] = ld_dsmem_f32(base + (uint32_t)(j * TC_BM * 4));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += t[j];
+        }
+        if (ok) {
+            if (p.res1_hi) {
+                const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o + c0);
+                const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o + c0);
+                add_split8(v, gh[0], gl[0]);
+                add_split8(v + 8, gh[1], gl[1]);
+            }
+            if (p.res2_hi) {
+                const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o + c0);
+                const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o + c0);
+                add_split8(v, gh[0], gl[0]);
+                add_split8(v + 8, gh[1], gl[1]);
+            }
+            store_split16(p.out_hi + o + c0, p.out_lo + o + c0, v, p.relu);
+        }
+    }
+}
+
 template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcMaps maps, const TcK p) {
     using Cfg = TcCfg<BN>;
@@ -399,6 +465,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();  // everything below reads activations / partials / tickets produced by earlier kernels
+    size_t cs_o = 0;      // cluster split-K: this thread's output offset / validity / tile row (epilogue warps)
+    bool cs_ok = false;
+    int cs_row = 0;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -480,6 +549,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         // ================= epilogue warps (TMEM lanes (warp % 4) * 32 ..) =================
         const int lg = warp & 3;
         const int row = lg * 32 + lane;  // row of the 128-pixel tile
+        cs_row = row;
         int it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
             const int t = w / p.nsplit, split = w - t * p.nsplit;
@@ -506,6 +576,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[ab]);
+            } else if (p.cluster_splitk) {
+                // one work item per CTA: the pipeline stages are idle once the accumulator is complete and stage 0 (64 KB) takes
+                // the partial tile; the sum happens after the cluster barrier below
+                tc_epilogue_park_smem<BN>(taddr, reinterpret_cast<float*>(smem), row, &tfull[ab], aphase);
+                cs_o = o;
+                cs_ok = ok;
             } else {
                 float* prow0 = p.partial + ((size_t)t * p.nsplit * TC_BM + row) * BN;  // split 0's row of this tile
                 tc_epilogue_park<BN>(taddr, prow0 + (size_t)split * TC_BM * BN, &tfull[ab], aphase);
@@ -524,6 +600,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 }
             }
         }
+    }
+    if (p.cluster_splitk) {
+        // every thread of every CTA of the cluster: partial tiles are in shared memory -> sum -> nobody leaves before all reads are done
+        __syncwarp();
+        cluster_sync_all();
+        if (warp >= 2) tc_epilogue_reduce_dsmem<BN>(p, reinterpret_cast<const float*>(smem), cs_row, (int)cluster_ctarank(), cs_o, cs_ok);
+        __syncwarp();
+        cluster_sync_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -997,26 +1081,83 @@ static bool tc_pdl_enabled() {
     return on;
 }
 
+static bool tc_cluster_splitk_enabled() {
+    static const bool on = getenv("QMRI_NO_CLUSTER_SPLITK") == nullptr;
+    return on;
+}
+
 template <int BN, int MODE>
-static int launch_tc(qmri_ctx* ctx, const TcMaps& maps, const TcK& k, int grid) {
+static int tc_configure() {
     static bool configured = false;
     if (!configured) {
         QCUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM));
         configured = true;
     }
+    return QMRI_OK;
+}
+
+// clusters of `cs` CTAs of this kernel that can be resident at once (one CTA per SM, a cluster inside one GPC); cached
+template <int BN, int MODE>
+static int tc_max_active_clusters(qmri_ctx* ctx, int cs) {
+    static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (cs < 2 || cs > 8) return 0;
+    if (cache[cs]) return cache[cs] < 0 ? 0 : cache[cs];
+    if (tc_configure<BN, MODE>() != QMRI_OK) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs * ctx->sm_count);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcCfg<BN>::SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tc_conv_kernel<BN, MODE>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    cache[cs] = n > 0 ? n : -1;
+    return n;
+}
+
+template <int BN, int MODE>
+static int launch_tc(qmri_ctx* ctx, const TcMaps& maps, const TcK& k, int grid) {
+    QCHECK((tc_configure<BN, MODE>()));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = TcCfg<BN>::SMEM;
     cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = tc_pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (k.cluster_splitk) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = k.nsplit;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     QCUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, MODE>, maps, k));
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
+}
+
+// split-K through a cluster: the largest split count whose clusters all fit the machine in one wave (0 = use the global workspace)
+template <int BN, int MODE>
+static int tc_cluster_split(qmri_ctx* ctx, int total_tiles, int KB) {
+    if (!tc_cluster_splitk_enabled()) return 0;
+    for (int ns = std::min(8, KB / 4); ns >= 2; --ns) {
+        if (total_tiles * ns > ctx->sm_count) continue;
+        if (total_tiles > tc_max_active_clusters<BN, MODE>(ctx, ns)) continue;
+        return ns;
+    }
+    return 0;
 }
 
 int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
@@ -1035,6 +1176,16 @@ int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
         if (nsplit > KB / 4) nsplit = KB / 4;
         if (nsplit > 8) nsplit = 8;
         if (nsplit < 1) nsplit = 1;
+    }
+    int cluster_splitk = 0;
+    if (nsplit > 1) {  // prefer the cluster variant: partial tiles meet in distributed shared memory instead of L2 + tickets
+        int cs = 0;
+        if (BN == 64) cs = p.mode == TC_CONV3X3 ? tc_cluster_split<64, 0>(ctx, total_tiles, KB) : p.mode == TC_DOWN2X2 ? tc_cluster_split<64, 1>(ctx, total_tiles, KB) : tc_cluster_split<64, 2>(ctx, total_tiles, KB);
+        else cs = p.mode == TC_CONV3X3 ? tc_cluster_split<128, 0>(ctx, total_tiles, KB) : p.mode == TC_DOWN2X2 ? tc_cluster_split<128, 1>(ctx, total_tiles, KB) : tc_cluster_split<128, 2>(ctx, total_tiles, KB);
+        if (cs >= 2) {
+            nsplit = cs;
+            cluster_splitk = 1;
+        }
     }
     const int work = total_tiles * nsplit;
     const int grid = work < ctx->sm_count ? work : ctx->sm_count;
@@ -1056,6 +1207,7 @@ int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
     k.S = p.S; k.H = p.H; k.W = p.W; k.Cin = p.Cin; k.Cout = p.Cout;
     k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
     k.relu = p.relu; k.nsplit = nsplit; k.trace = nullptr;
+    k.cluster_splitk = cluster_splitk;
     if (BN == 64) {
         if (p.mode == TC_CONV3X3) return launch_tc<64, 0>(ctx, maps, k, grid);
         if (p.mode == TC_DOWN2X2) return launch_tc<64, 1>(ctx, maps, k, grid);
@@ -1180,7 +1332,7 @@ int conv3x3_tc_pair(qmri_ctx* ctx, const TcConvParams& p) {
     k.partial = p.partial; k.tickets = p.tickets;
     k.S = p.S; k.H = p.H; k.W = p.W; k.Cin = p.Cin; k.Cout = p.Cout;
     k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
-    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr;
+    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr; k.cluster_splitk = 0;
     if (p.Cout == 64) return launch_pair<128, 1>(ctx, p, k);
     if (p.Cout == 128) return launch_pair<256, 1>(ctx, p, k);
     return launch_pair<256, 0>(ctx, p, k);
