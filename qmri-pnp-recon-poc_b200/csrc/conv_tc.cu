@@ -107,12 +107,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -136,10 +130,6 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // arrive on the mbarrier at the same shared-memory offset in every CTA of `mask` once the MMAs issued so far have completed
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
-}
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 inputs, fp32 accumulate)
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -375,7 +365,7 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
     asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t mapa_rank_early(uint32_t saddr, uint32_t rank) {
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
@@ -392,7 +382,7 @@ __device__ __forceinline__ void tc_epilogue_reduce_dsmem(const TcK& p, const flo
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
 #pragma unroll 1
         for (int s = 0; s < p.nsplit; ++s) {
-            const uint32_t base = mapa_rank_early(mine, (uint32_t)s) + (uint32_t)((c0 * TC_BM + row) * 4);
+            const uint32_t base = mapa_cluster(mine, (uint32_t)s) + (uint32_t)((c0 * TC_BM + row) * 4);
             float t[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) t[j] = ld_dsmem_f32(base + (uint32_t)(j * TC_BM * 4));

@@ -80,7 +80,7 @@ struct K1Tables {
     // streaming kernel (xupdate_stream.cu): work items of the sparse m-direction sums (see build_stream_tables)
     bool stream_ok = false;           // false: some frame needs more than 224 items / too many overflow partials
     std::vector<uint32_t> itA;        // [C][N] k1 | cnt << 8 | start << 16   (k1 == 255: thread has no item)
-    std::vector<uint32_t> itB;        // [C][N] slot | novf << 8 | ovf0 << 16 | zrow << 24   (zrow == 255: none)
+    std::vector<uint32_t> itB;        // [C][N] slot | novf << 8 | ovf0 << 16
     std::vector<uint32_t> ent;        // [nmeas] j | k2 << 16, frame-major, grouped by item
     std::vector<uint16_t> rowmask;    // [C][16] bit a of entry b: row 14 a + b holds samples (inverse FFT stage 1 skips empty rows)
     int n_ovf = 0;                    // largest number of overflow partials in one frame
@@ -109,7 +109,7 @@ constexpr int STREAM_OVF_MAX = 96;   // == k1::OVF_MAX_STREAM
 static inline void build_stream_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t, int q_min = 1) {
     t.stream_ok = (N % 16 == 0) && N <= 254;
     t.itA.assign((size_t)t.C * N, 255u);
-    t.itB.assign((size_t)t.C * N, 255u << 24);
+    t.itB.assign((size_t)t.C * N, 0u);
     t.ent.assign(std::max(t.nmeas, 1), 0);
     t.rowmask.assign((size_t)t.C * 16, 0);
     t.n_ovf = 0;
@@ -167,10 +167,10 @@ static inline void build_stream_tables(int N, const std::vector<std::vector<int3
         std::stable_sort(left.begin(), left.end(), [&](int a, int b2) { return items[a].cnt > items[b2].cnt; });
         for (int tid = 0, q = 0; tid < N && q < (int)left.size(); ++tid)
             if (place[tid] < 0) place[tid] = left[q++];
-        std::vector<int> zrow(N, 255);  // (rows without samples are skipped by the inverse FFT through `rowmask`: no zero fill)
+        // (rows without samples are skipped by the inverse FFT through `rowmask`: no zero fill)
         size_t pos = 0;
         for (int tid = 0; tid < N; ++tid) {
-            uint32_t A = 255u, B = (uint32_t)zrow[tid] << 24;
+            uint32_t A = 255u, B = 0u;
             if (place[tid] >= 0) {
                 const Item& it = items[place[tid]];
                 A = (uint32_t)it.k1 | ((uint32_t)it.cnt << 8) | ((uint32_t)pos << 16);

@@ -32,7 +32,7 @@ struct K1Params {
     const float2* tw2;       // [16][16] e^{-2 pi i (i j) / 224}
     const float2* tw448;     // [448] e^{-2 pi i t / 448}
     const uint32_t* itA;     // [C][224] work item of thread tid: k1 | cnt << 8 | start << 16
-    const uint32_t* itB;     // [C][224] slot | novf << 8 | ovf0 << 16 | zrow << 24
+    const uint32_t* itB;     // [C][224] slot | novf << 8 | ovf0 << 16
     const uint32_t* ent;     // [nmeas] j | k2 << 16, frame-major, grouped by item
     const uint16_t* rowmask; // [C][16] non-empty rows, by inverse-FFT lane
     int n_ovf;               // overflow partials per frame (sizes the shared-memory slots)

@@ -376,12 +376,9 @@ QHD void p4_item_spill(float2* o, const float2 (&SP)[NP_STREAM], const float2 (&
         o[NP_STREAM + d] = SM[d];
     }
 }
-QHD void p4_zero_row(float2* ws, int k1) {
-#pragma unroll
-    for (int mm = 0; mm < HC_STREAM; ++mm) ws[mm * CS + k1] = make_float2(0.f, 0.f);
-}
 
 // item table words (op_tables.h): A = k1 | cnt << 8 | start << 16 (k1 == 255: no item);
-//                                 B = slot | novf << 8 | ovf0 << 16 | zrow << 24 (slot 0: primary; zrow == 255: none)
+//                                 B = slot | novf << 8 | ovf0 << 16 (slot 0: primary; bits 24-31 unused: rows without samples are
+//                                     skipped by the inverse FFT through the row mask)
 
 }  // namespace k1

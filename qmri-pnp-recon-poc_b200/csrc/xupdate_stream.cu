@@ -43,7 +43,7 @@ __device__ __forceinline__ size_t late_offset(size_t off, float after) {
 }
 
 struct Item {
-    int k1, cnt, start, slot, novf, ovf0, zrow;
+    int k1, cnt, start, slot, novf, ovf0;
 };
 __device__ __forceinline__ Item decode_item(uint32_t A, uint32_t B) {
     Item it;
@@ -53,7 +53,6 @@ __device__ __forceinline__ Item decode_item(uint32_t A, uint32_t B) {
     it.slot = (int)(B & 0xffu);          // 0: primary item of its row
     it.novf = (int)((B >> 8) & 0xffu);
     it.ovf0 = (int)((B >> 16) & 0xffu);
-    it.zrow = (int)(B >> 24);            // 255: no zero-fill duty
     return it;
 }
 
