@@ -1066,15 +1066,9 @@ int tc_block_n(int Cout) { return Cout == 64 ? 64 : 128; }
 size_t tc_partial_elems(int sm_count) { return (size_t)sm_count * TC_BM * 256; }
 size_t tc_ticket_count(int sm_count) { return (size_t)sm_count * 4; }
 
-static bool tc_pdl_enabled() {
-    static const bool on = getenv("QMRI_NO_PDL") == nullptr;
-    return on;
-}
+static bool tc_pdl_enabled() { return getenv("QMRI_NO_PDL") == nullptr; }  // read per call: tests toggle it
 
-static bool tc_cluster_splitk_enabled() {
-    static const bool on = getenv("QMRI_NO_CLUSTER_SPLITK") == nullptr;
-    return on;
-}
+static bool tc_cluster_splitk_enabled() { return getenv("QMRI_NO_CLUSTER_SPLITK") == nullptr; }  // read per call: tests toggle it
 
 template <int BN, int MODE>
 static int tc_configure() {

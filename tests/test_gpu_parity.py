@@ -246,6 +246,29 @@ def test_denoiser_matches_cpu_forward(q, nets, shape, precision):
     assert err <= TOL_DENOISER
 
 
+def test_denoiser_split_k_fallback_and_launch_modes(q, nets, monkeypatch):
+    """One slice splits K at the 256- and 512-channel levels: through a thread-block cluster (default) or the L2 workspace with
+    tickets (QMRI_NO_CLUSTER_SPLITK); with and without programmatic dependent launch.  All within the denoiser tolerance."""
+    import torch
+    from oracle import unetres
+    net, sd = nets
+    net.set_precision("tc")
+    rng = np.random.default_rng(11)
+    x = rng.random((1, 10, 224, 224)).astype(np.float32)
+    with torch.no_grad():
+        ref = unetres.unetres_forward(sd, torch.from_numpy(x)).numpy()
+    y0 = net.forward(x)
+    monkeypatch.setenv("QMRI_NO_CLUSTER_SPLITK", "1")
+    y1 = net.forward(x)
+    monkeypatch.setenv("QMRI_NO_PDL", "1")
+    y2 = net.forward(x)
+    monkeypatch.delenv("QMRI_NO_CLUSTER_SPLITK")
+    y3 = net.forward(x)
+    assert np.array_equal(y1, y2) and np.array_equal(y0, y3)      # dependent launch changes timing only
+    assert rel_l2(y0, y1) <= 1e-5                                  # other split counts: another summation order
+    assert rel_l2(y0, ref) <= TOL_DENOISER and rel_l2(y1, ref) <= TOL_DENOISER
+
+
 def test_denoiser_matlab_layout_and_wrapper(q, nets):
     from oracle import unetres
     net, sd = nets
