@@ -398,6 +398,18 @@ def test_admm_loop_batched_slices_are_independent(q, ops):
         assert rel_l2(x[..., s], xo) <= TOL_XUPDATE
 
 
+def test_admm_loop_batched_epi(q, ops):
+    """BASELINE configs[2] shape in small: a slice batch on the EPI mask takes the streaming kernels (row chunks + overflow slots)."""
+    from oracle.admm import pnp_admm
+    P, Po = ops["epi"]
+    Fo, Xgt, Y, X0 = make_problem(Po, 26, S=3)
+    param = {"iter": 4, "gamma": 0.05, "denoiser_type": "single_level"}
+    x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=box_denoiser, X0=X0))
+    for s in range(3):
+        xo = pnp_admm(Y[:, s], dict(param, F=Fo, net=box_denoiser, X0=X0[..., s]), solver="exact")
+        assert rel_l2(x[..., s], xo) <= TOL_XUPDATE
+
+
 def test_admm_iter_counts_zero_and_one(q, ops):
     P, Po = ops["spiral"]
     Fo, Xgt, Y, X0 = make_problem(Po, 23)
