@@ -8,7 +8,7 @@ B200 raises.
 from ._capi import (QMRI_C128, QMRI_C64, QMRI_DEVICE, QMRI_F32, QMRI_F64, QMRI_HOST, Context, QmriError,
                     load_library)
 from .admm import AdmmSession, PnP_ADMM
-from .denoiser import UNetRes, build_noise_map, denoiseImage_PnP_ADMM, state_dict_keys
+from .denoiser import UNetRes, build_noise_map, denoiseImage_PnP_ADMM, load_checkpoint_state_dict, state_dict_keys
 from .matching import Dictionary, mrf_dtm, mrf_dtm_cpu, synthesize_tsmis
 from .sharding import allreduce_keys, atom_shard, mrf_dtm_sharded, pack_keys, slice_shard, unpack_keys
 from .operators import (FOperator, SubsamplingPattern, fft_operator, setup_subsampling_epi,

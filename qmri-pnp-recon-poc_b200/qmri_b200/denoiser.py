@@ -43,9 +43,41 @@ def state_dict_keys(in_nc=10):
     return keys
 
 
+def load_checkpoint_state_dict(path_or_obj):
+    """Weights of a trained ``UNetRes`` as the reference saves them: ``torch.save({'model_state_dict': net.state_dict(),
+    'epoch': ..., 'loss': ...}, path)`` (``PyTorch_Denoiser/main_train.py``; read back at ``main_test.py:260-262``).
+    Accepts the path of such a file, the loaded dict, or a bare ``state_dict``; strips ``module.`` prefixes left by
+    ``DataParallel``.  Returns ``(state_dict, in_nc)`` with ``in_nc`` read off ``m_head.weight``."""
+    obj = path_or_obj
+    if isinstance(obj, (str, bytes)) or hasattr(obj, "__fspath__"):
+        import torch
+        obj = torch.load(obj, map_location="cpu", weights_only=True)
+    if not isinstance(obj, dict):
+        raise TypeError("checkpoint must be a dict (state_dict, or a dict holding 'model_state_dict')")
+    for k in ("model_state_dict", "state_dict", "model"):
+        if k in obj and isinstance(obj[k], dict):
+            obj = obj[k]
+            break
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in obj.items()}
+    if "m_head.weight" not in sd:
+        raise KeyError("checkpoint holds no UNetRes weights (m_head.weight missing)")
+    in_nc = int(tuple(sd["m_head.weight"].shape)[1])
+    want = dict(state_dict_keys(in_nc))
+    extra = [k for k in sd if k not in want]
+    if extra:
+        raise KeyError(f"unexpected tensors in the checkpoint (this build runs the bias-free UNetRes of main_train.py:247): {extra[:4]}")
+    return sd, in_nc
+
+
 class UNetRes:
     """The built-in on-device denoiser.  ``state_dict`` maps the reference's keys to arrays
     (numpy or torch tensors)."""
+
+    @classmethod
+    def from_checkpoint(cls, path_or_obj, ctx=None):
+        """Trained-weight import (``main_test.py:260-262``): see ``load_checkpoint_state_dict``."""
+        sd, in_nc = load_checkpoint_state_dict(path_or_obj)
+        return cls(sd, in_nc=in_nc, ctx=ctx)
 
     def __init__(self, state_dict, in_nc=10, ctx=None):
         self.ctx = ctx or Context.default()

@@ -40,3 +40,23 @@ def test_denoise_wrapper_validates_input():
     A = np.random.default_rng(0).random((8, 8, 10))
     assert np.array_equal(q.denoiseImage_PnP_ADMM(A, Net(), True, False), A)
     assert np.allclose(q.denoiseImage_PnP_ADMM(A, Net(), True, True), 0)
+
+
+def test_checkpoint_import_reads_the_reference_format(tmp_path):
+    """main_test.py:260-262 loads {'model_state_dict', 'epoch', 'loss'}; DataParallel prefixes and bare state_dicts are accepted too."""
+    import torch
+    import qmri_b200 as q
+    from oracle import unetres
+    sd = unetres.make_state_dict(11, seed=3)
+    f = tmp_path / "ckpt.pt"
+    torch.save({"model_state_dict": sd, "epoch": 7, "loss": 0.1}, f)
+    got, in_nc = q.load_checkpoint_state_dict(str(f))
+    assert in_nc == 11 and set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    got2, in_nc2 = q.load_checkpoint_state_dict({"module." + k: v for k, v in sd.items()})
+    assert in_nc2 == 11 and set(got2) == set(sd)
+    assert [k for k, _ in q.state_dict_keys(11)] == list(sd.keys())        # same key order as UNetRes(...).state_dict()
+    import pytest
+    with pytest.raises(KeyError):
+        q.load_checkpoint_state_dict({"m_head.weight": sd["m_head.weight"], "m_head.bias": torch.zeros(64)})
+    with pytest.raises(KeyError):
+        q.load_checkpoint_state_dict({"something": torch.zeros(1)})
