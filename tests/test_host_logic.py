@@ -60,3 +60,18 @@ def test_checkpoint_import_reads_the_reference_format(tmp_path):
         q.load_checkpoint_state_dict({"m_head.weight": sd["m_head.weight"], "m_head.bias": torch.zeros(64)})
     with pytest.raises(KeyError):
         q.load_checkpoint_state_dict({"something": torch.zeros(1)})
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, no GPU): one JSON line with the contract's keys."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-iters", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 1 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["metric"].startswith("ADMM slice-iterations/s") and line["unit"] == "slice-iterations/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
