@@ -253,7 +253,7 @@ constexpr int HT_TW = 32, HT_PITCH = 36;   // tile width; patch row pitch in flo
 constexpr int HEAD_WPITCH = 80;            // weights [9][Cin][4 cb][20]: 20-float blocks put the four cb lanes on different banks
 // TH = tile height (8, or 4 for one or two slices: twice the CTAs for 148 SMs); CTA = 32 TH threads.
 template <int TH>
-__global__ void __launch_bounds__(32 * TH) head_fp32_kernel(HeadTailParams p) {
+__global__ void __launch_bounds__(32 * TH, (TH == 8 ? 3 : 1)) head_fp32_kernel(HeadTailParams p) {
     constexpr int HEAD_TH = TH, HEAD_ROWS = TH + 2, NT = 32 * TH;
     extern __shared__ __align__(16) float hsm[];
     const int Cin = p.Cin;
