@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(32 * TH, (TH == 8 ? 3 : 1)) head_fp32_kernel(H
 // pixel tile (196 per slice); K = 64 is staged in four chunks of 16 channels.  Patch planes are 10 x 36 floats: 360 = 8 mod 32
 // puts the four kq lanes on different banks.
 template <int TH>
-__global__ void __launch_bounds__(32 * TH) tail_fp32_kernel(HeadTailParams p) {
+__global__ void __launch_bounds__(32 * TH, (TH == 8 ? 4 : 1)) tail_fp32_kernel(HeadTailParams p) {
     constexpr int TAIL_TH = TH, TAIL_ROWS = TH + 2, TAIL_PLANE = TAIL_ROWS * HT_PITCH, NT = 32 * TH;
     static_assert(TAIL_PLANE % 32 == 8 || TAIL_PLANE % 32 == 24, "the four kq lanes must land on different banks");
     __shared__ __align__(16) float patch[16 * TAIL_PLANE];   // [16][10][36]
