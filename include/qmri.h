@@ -101,6 +101,22 @@ int64_t qmri_op_nmeas(const qmri_op* op);
  * callers pin the mask constructors against the reference's `find` output. */
 int qmri_op_indices(const qmri_op* op, int32_t* idx, int64_t* frame_ptr);
 
+/* The bare sampling matrix the constructors return as handles (setup_subsampling_spiralgrided.m:36-42,
+ * setup_subsampling_epi.m:31-35): P = vertical stack of S_i * kron(conj(V(i,:)), I).
+ *   y = P.for(vec):  vec = N*M*C k-space column (reshape(fft2(x),[],1)), y = nmeas complex
+ *   vec = P.adj(y):  P' * y
+ * Both run on the device in double precision (a gather / scatter; exact for V = eye(C)). */
+int qmri_op_for(qmri_op* op, const void* kvec, int k_dtype, void* y, int y_dtype);
+int qmri_op_adj(qmri_op* op, const void* y, int y_dtype, void* kvec, int k_dtype);
+
+/* Y = awgn(Y, snr, 'measured')   main_recon_tsmis_FFT.m:243
+ * In place on an nmeas x S interleaved complex array: complex white Gaussian noise of power
+ * mean(|Y(:,s)|^2) / 10^(snr_db/10) per slice, Philox-4x32-10 counter (sample, slice) keyed by `seed`, Box-Muller in double:
+ * the same seed gives the same noise whatever the batch size.  (MATLAB's generator is not reproduced: statistical equality only.) */
+int qmri_awgn(qmri_ctx* ctx, void* y, int y_dtype, int64_t nmeas, int S, double snr_db, uint64_t seed);
+/* Device-resident variant: y_dev = float2 [S][nmeas]; power_dev = S doubles of scratch (receives mean |y|^2 per slice). */
+int qmri_awgn_dev(qmri_ctx* ctx, float* y_dev, int64_t nmeas, int S, double snr_db, uint64_t seed, double* power_dev);
+
 /* y = F.forward(x)   main_recon_tsmis_FFT.m:228   x: N x M x C x S (real or complex), y: nmeas x S complex */
 int qmri_forward(qmri_op* op, const void* x, int x_dtype, int S, void* y, int y_dtype);
 /* x = F.adjoint(y)   main_recon_tsmis_FFT.m:229   y: nmeas x S complex, x: N x M x C x S complex */
@@ -177,6 +193,12 @@ int qmri_admm_xupdate_only(qmri_admm* st, int reps);
  * handle (the whole dictionary when 0,K); D/normD/lut are kept whole for the gathers. */
 int qmri_dict_load(qmri_ctx* ctx, const float* D, const float* normD, const float* lut, int64_t K, int C, int Q,
                    int64_t shard_begin, int64_t shard_end, qmri_dict** out);
+/* Atom-sharded residency (BASELINE config 5: a dictionary too large for one GPU): D_shard holds ONLY the rows
+ * [shard_begin, shard_end) ((shard_end - shard_begin) x C column-major); normD / lut stay whole (12 B per atom).
+ * qmri_match_finish_dev on such a handle writes the pixels whose winning atom it owns and zeros elsewhere, so the
+ * per-rank outputs combine with a sum all-reduce (every pixel has exactly one owner). */
+int qmri_dict_load_shard(qmri_ctx* ctx, const float* D_shard, const float* normD, const float* lut, int64_t K, int C, int Q,
+                         int64_t shard_begin, int64_t shard_end, qmri_dict** out);
 int qmri_dict_destroy(qmri_dict* d);
 /* x: npix x C column-major, real or complex.  Outputs (any may be NULL, cf. par.f.*):
  * qmap npix x Q float (NaN -> 0, :139), pd npix complex float interleaved (:96), mt npix float
@@ -199,6 +221,20 @@ int qmri_match_finish_dev(qmri_dict* d, const float* x_re, const float* x_im, in
  * qmap: npix x 3 column-major (T1,T2,PD) host float32 -> X npix x C column-major float32;
  * atom_index (optional): 1-based I.  Exact distance ties resolve to the lowest atom index. */
 int qmri_synthesize(qmri_dict* d, const float* qmap, int64_t npix, float* X, int32_t* atom_index);
+
+/* ---- foreground mask and quality metrics ------------------------------
+ * mask = getmask_fromPD(PD, thresh)   main_files/utils/getmask_fromPD.m:1-15 (called at main_recon_tsmis_FFT.m:190):
+ * |PD| / max, values below thresh zeroed, holes filled (8-connected background), binarised.  pd: N x M column-major,
+ * real or complex; mask: N x M float 0/1. */
+int qmri_foreground_mask(qmri_ctx* ctx, const void* pd, int pd_dtype, int N, int M, double thresh, float* mask);
+/* The metrics block of main_recon_tsmis_FFT.m:328-384, computed on the device in double:
+ *   qmap  N x M x 3 = cat(3, out.qmap, out.pd) (T1, T2, PD; real or complex), qmap0 the ground truth, mask from
+ *   qmri_foreground_mask (NULL = all ones); X, X0: N x M x C reconstructed / ground-truth TSMIs (both NULL to skip).
+ *   out[11] = tsmi_mean_psnr, tsmi_mean_ssim, t1_mae, t1_psnr, t1_ssim, t2_mae, t2_psnr, t2_ssim, pd_mae, pd_psnr, pd_ssim
+ * with MATLAB's psnr (peak 1 for double images) and ssim defaults (11 x 11 Gaussian window, sigma 1.5, replicate
+ * padding, dynamic range 1). */
+int qmri_recon_metrics(qmri_ctx* ctx, int N, int M, int C, const void* qmap, int qmap_dtype, const void* qmap0, int qmap0_dtype,
+                       const float* mask, const void* X, int x_dtype, const void* X0, int x0_dtype, double* out);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,11 @@ struct qmri_ctx {
 
 extern thread_local char g_qmri_err[512];
 
+// per-device caches (cudaFuncSetAttribute opt-ins, occupancy queries) are indexed by qmri_ctx::device: the attribute is per device
+// and one process may hold contexts on several GPUs
+constexpr int QMRI_MAX_DEV = 64;
+static inline int qmri_dev_slot(const qmri_ctx* ctx) { return ctx->device & (QMRI_MAX_DEV - 1); }
+
 static inline int qmri_fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

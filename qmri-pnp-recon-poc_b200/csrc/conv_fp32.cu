@@ -481,7 +481,8 @@ static inline int ht_tile_h(const HeadTailParams& p) { return p.S <= 2 ? 4 : 8; 
 template <int TH>
 static int head_launch(qmri_ctx* ctx, const HeadTailParams& p) {
     size_t smem = (size_t)(p.Cin * (TH + 2) * HT_PITCH + 9 * p.Cin * HEAD_WPITCH) * sizeof(float);
-    static size_t configured = 0;
+    static size_t configured_dev[QMRI_MAX_DEV] = {};
+    size_t& configured = configured_dev[qmri_dev_slot(ctx)];
     if (smem > 48 * 1024 && smem > configured) {
         QCUDA(cudaFuncSetAttribute(head_fp32_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

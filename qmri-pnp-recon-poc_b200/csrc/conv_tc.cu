@@ -1071,8 +1071,9 @@ static bool tc_pdl_enabled() { return getenv("QMRI_NO_PDL") == nullptr; }  // re
 static bool tc_cluster_splitk_enabled() { return getenv("QMRI_NO_CLUSTER_SPLITK") == nullptr; }  // read per call: tests toggle it
 
 template <int BN, int MODE>
-static int tc_configure() {
-    static bool configured = false;
+static int tc_configure(qmri_ctx* ctx) {
+    static bool configured_dev[QMRI_MAX_DEV] = {};
+    bool& configured = configured_dev[qmri_dev_slot(ctx)];
     if (!configured) {
         QCUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM));
         configured = true;
@@ -1083,10 +1084,11 @@ static int tc_configure() {
 // clusters of `cs` CTAs of this kernel that can be resident at once (one CTA per SM, a cluster inside one GPC); cached
 template <int BN, int MODE>
 static int tc_max_active_clusters(qmri_ctx* ctx, int cs) {
-    static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    static int cache_dev[QMRI_MAX_DEV][9] = {};
+    int* cache = cache_dev[qmri_dev_slot(ctx)];
     if (cs < 2 || cs > 8) return 0;
     if (cache[cs]) return cache[cs] < 0 ? 0 : cache[cs];
-    if (tc_configure<BN, MODE>() != QMRI_OK) return 0;
+    if (tc_configure<BN, MODE>(ctx) != QMRI_OK) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs * ctx->sm_count);
     cfg.blockDim = dim3(TC_THREADS);
@@ -1109,7 +1111,7 @@ static int tc_max_active_clusters(qmri_ctx* ctx, int cs) {
 
 template <int BN, int MODE>
 static int launch_tc(qmri_ctx* ctx, const TcMaps& maps, const TcK& k, int grid) {
-    QCHECK((tc_configure<BN, MODE>()));
+    QCHECK((tc_configure<BN, MODE>(ctx)));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(TC_THREADS);
@@ -1236,7 +1238,8 @@ void tc_pair_weight_boxes(int Cout, int* rows_main, int* rows_h2) {
 template <int NA, int STACK>
 static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
     using Cfg = PairCfg<NA, STACK>;
-    static bool configured = false;
+    static bool configured_dev[QMRI_MAX_DEV] = {};
+    bool& configured = configured_dev[qmri_dev_slot(ctx)];
     if (!configured) {
         QCUDA(cudaFuncSetAttribute(tc_conv3x3_pair_kernel<NA, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;

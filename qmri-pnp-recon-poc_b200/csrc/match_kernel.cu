@@ -146,6 +146,14 @@ __global__ void match_finish_kernel(K2Finish p) {
     unsigned long long key = p.keys[pix];
     int64_t idx = (int64_t)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
     if (key == 0ull || idx >= p.K) idx = 0;  // all-NaN pixel: MATLAB's max returns index 1
+    if (idx < p.own0 || idx >= p.own1) {       // atom-sharded dictionary: the owner of the winning atom writes this pixel
+        if (p.pd) p.pd[2 * pix] = p.pd[2 * pix + 1] = 0.f;
+        if (p.mt) p.mt[pix] = 0.f;
+        if (p.dm) p.dm[pix] = 0;
+        if (p.qmap)
+            for (int q = 0; q < p.Q; ++q) p.qmap[(int64_t)q * p.npix + pix] = 0.f;
+        return;
+    }
     float sr = 0.f, si = 0.f;
     for (int c = 0; c < p.C; ++c) {
         float d = __ldg(p.Dp + idx * p.CP + c);
@@ -174,7 +182,8 @@ int launch_c(qmri_ctx* ctx, const K2Params& p) {
     int64_t gx = (p.npix + ppb - 1) / ppb;
     // split the atom range so that the grid fills whole waves of resident CTAs (small pixel counts would
     // otherwise leave SMs idle or end with a mostly empty last wave)
-    static int per_sm = 0;
+    static int per_sm_dev[QMRI_MAX_DEV] = {};
+    int& per_sm = per_sm_dev[qmri_dev_slot(ctx)];
     if (!per_sm) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel<C, CP, PX, true>, K2_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     }

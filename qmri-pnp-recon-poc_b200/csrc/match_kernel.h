@@ -28,6 +28,7 @@ struct K2Finish {
     float* pd;           // [npix][2]
     float* mt;           // [npix]
     int32_t* dm;         // [npix], 1-based
+    int64_t own0, own1;  // atoms whose rows are resident here: pixels won by another rank's atom get zeros (summed over ranks later)
 };
 
 int k2_padded_channels(int C);

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "aux_kernels.h"
 #include "common.cuh"
 #include "conv_kernels.h"
 #include "match_kernel.h"
@@ -287,6 +288,9 @@ struct qmri_op {
     // scratch for the host entry points
     DevBuf stage, a_re, a_im, b_re, b_im, c_re, c_im, ybuf, mm_ord, mm_f;
     DevBuf k1_part, k1_cbuf;  // streaming x-update: partial sample sums / solved samples
+    // the bare sampling matrix (P.for / P.adj): uploaded on first use
+    std::vector<double> hV;   // L x C column-major (empty: identity)
+    DevBuf p_idx, p_fp, p_V, p_k, p_y, p_stage;
     size_t plane() const { return (size_t)N * M * C; }
 };
 
@@ -328,6 +332,7 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     const int q_min = env ? atoi(env) : 8;  // 8: measured best on the spiral masks (fewer overflow partials)
     optab::build_k1_tables(N, frames, op->t, q_min);
     op->general = !identity;
+    if (!identity) op->hV.assign(V, V + (size_t)L * C);
     if (op->general) {
         optab::build_general_tables(N, frames, V, L, C, op->g, q_min);
         if (!op->g.ok) {
@@ -429,6 +434,7 @@ extern "C" int qmri_op_destroy(qmri_op* op) {
     op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
     op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
     op->k1_part.release(); op->k1_cbuf.release();
+    op->p_idx.release(); op->p_fp.release(); op->p_V.release(); op->p_k.release(); op->p_y.release(); op->p_stage.release();
     delete op;
     return QMRI_OK;
 }
@@ -983,6 +989,9 @@ extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
         } else {
             QCHECK(admm_k1(st, k == iters - 1));
         }
+        // PnP_ADMM.m:121-144 also denoise after the last x-update, but only x is returned (:148): v and u of the last iteration
+        // are dead, so the final 64-layer forward is skipped
+        if (k == iters - 1) return QMRI_OK;
         minmax_finalize_kernel<<<nblk(S, 128), 128, 0, ctx->stream>>>(st->mm_ord.as<int>(), st->mm_f.as<float>(), S);
         QLAUNCH_CHECK(ctx);
         return admm_denoise(st);
@@ -1015,6 +1024,9 @@ extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
                 cudaGetLastError();
                 st->graph = nullptr;
                 st->graph_failed = true;  // fall back to direct launches for the rest of this state's life
+                fprintf(stderr, "libqmri_b200: warning: CUDA graph capture of the ADMM iteration failed (%s, rc %d); this session "
+                                "continues with direct kernel launches (slower at small slice batches)\n",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "no error code", rc);
                 ctx->launches = l0;
                 QCHECK(iteration(k));
                 for (++k; k < iters; ++k) QCHECK(iteration(k));
@@ -1073,11 +1085,13 @@ struct qmri_dict {
     int64_t K = 0, a0 = 0, a1 = 0;
     int C = 0, CP = 0, Q = 0;
     float *Dp = nullptr, *normD = nullptr, *lut = nullptr;
+    float* Dp_alloc = nullptr;  // what cudaMalloc returned; Dp = Dp_alloc - a0 * CP when only the shard's atoms are resident
+    bool shard_only = false;    // D holds atoms [a0, a1) only: finish writes the pixels whose winner this handle owns, zeros elsewhere
     DevBuf stage, x_re, x_im, keys, qmap, pd, mt, dm;
 };
 
-extern "C" int qmri_dict_load(qmri_ctx* ctx, const float* D, const float* normD, const float* lut, int64_t K, int C, int Q,
-                              int64_t shard_begin, int64_t shard_end, qmri_dict** out) {
+static int dict_load(qmri_ctx* ctx, const float* D, const float* normD, const float* lut, int64_t K, int C, int Q,
+                     int64_t shard_begin, int64_t shard_end, bool shard_only, qmri_dict** out) {
     if (!ctx || !D || !normD || !lut || !out) return qmri_fail(QMRI_EINVAL, "qmri_dict_load: null argument");
     if (K < 1 || K >= 0xFFFFFFFFll) return qmri_fail(QMRI_EINVAL, "dictionary size K = %lld out of range", (long long)K);
     if (C < 1 || C > 16) return qmri_fail(QMRI_EUNSUPPORTED, "dictionary matching supports 1..16 channels (got %d)", C);
@@ -1088,15 +1102,21 @@ extern "C" int qmri_dict_load(qmri_ctx* ctx, const float* D, const float* normD,
     d->ctx = ctx;
     d->K = K; d->C = C; d->Q = Q; d->a0 = shard_begin; d->a1 = shard_end;
     d->CP = k2_padded_channels(C);
-    std::vector<float> Dp((size_t)K * d->CP, 0.f);
+    d->shard_only = shard_only;
+    // rows resident on this device: the whole dictionary, or atoms [a0, a1) only (D then holds just those rows)
+    const int64_t R = shard_only ? shard_end - shard_begin : K;
+    std::vector<float> Dp((size_t)R * d->CP, 0.f);
     for (int c = 0; c < C; ++c)
-        for (int64_t k = 0; k < K; ++k) Dp[(size_t)k * d->CP + c] = D[(size_t)c * K + k];
-    int r = dev_alloc(&d->Dp, Dp.size()) | dev_alloc(&d->normD, (size_t)K) | dev_alloc(&d->lut, (size_t)K * Q);
+        for (int64_t k = 0; k < R; ++k) Dp[(size_t)k * d->CP + c] = D[(size_t)c * R + k];
+    int r = dev_alloc(&d->Dp_alloc, Dp.size()) | dev_alloc(&d->normD, (size_t)K) | dev_alloc(&d->lut, (size_t)K * Q);
     if (r) {
         qmri_dict_destroy(d);
         return QMRI_ENOMEM;
     }
-    cudaMemcpy(d->Dp, Dp.data(), Dp.size() * 4, cudaMemcpyHostToDevice);
+    // kernels index atoms globally: with a resident shard the base pointer is shifted so that row a0 is the first resident row
+    // (rows outside [a0, a1) are never dereferenced: the scoring range is the shard and finish checks ownership)
+    d->Dp = shard_only ? d->Dp_alloc - (ptrdiff_t)shard_begin * d->CP : d->Dp_alloc;
+    cudaMemcpy(d->Dp_alloc, Dp.data(), Dp.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(d->normD, normD, (size_t)K * 4, cudaMemcpyHostToDevice);
     cudaError_t e = cudaMemcpy(d->lut, lut, (size_t)K * Q * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -1106,11 +1126,19 @@ extern "C" int qmri_dict_load(qmri_ctx* ctx, const float* D, const float* normD,
     *out = d;
     return QMRI_OK;
 }
+extern "C" int qmri_dict_load(qmri_ctx* ctx, const float* D, const float* normD, const float* lut, int64_t K, int C, int Q,
+                              int64_t shard_begin, int64_t shard_end, qmri_dict** out) {
+    return dict_load(ctx, D, normD, lut, K, C, Q, shard_begin, shard_end, false, out);
+}
+extern "C" int qmri_dict_load_shard(qmri_ctx* ctx, const float* D_shard, const float* normD, const float* lut, int64_t K, int C, int Q,
+                                    int64_t shard_begin, int64_t shard_end, qmri_dict** out) {
+    return dict_load(ctx, D_shard, normD, lut, K, C, Q, shard_begin, shard_end, true, out);
+}
 extern "C" int qmri_dict_destroy(qmri_dict* d) {
     if (!d) return QMRI_OK;
     DevSetter ds(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
-    cudaFree(d->Dp); cudaFree(d->normD); cudaFree(d->lut);
+    cudaFree(d->Dp_alloc); cudaFree(d->normD); cudaFree(d->lut);
     d->stage.release(); d->x_re.release(); d->x_im.release(); d->keys.release();
     d->qmap.release(); d->pd.release(); d->mt.release(); d->dm.release();
     delete d;
@@ -1136,6 +1164,8 @@ extern "C" int qmri_match_finish_dev(qmri_dict* d, const float* x_re, const floa
     K2Finish f = {};
     f.x_re = x_re; f.x_im = x_im; f.npix = npix; f.Dp = d->Dp; f.normD = d->normD; f.lut = d->lut;
     f.K = d->K; f.C = d->C; f.CP = d->CP; f.Q = d->Q; f.keys = (const unsigned long long*)keys_dev;
+    f.own0 = d->shard_only ? d->a0 : 0;
+    f.own1 = d->shard_only ? d->a1 : d->K;
     f.qmap = qmap_dev; f.pd = pd_dev; f.mt = mt_dev; f.dm = dm_dev;
     return k2_launch_finish(d->ctx, f);
 }
@@ -1152,7 +1182,7 @@ extern "C" int qmri_match(qmri_dict* d, const void* x, int x_dtype, int64_t npix
     if (!d || (!x && npix > 0)) return qmri_fail(QMRI_EINVAL, "qmri_match: null argument");
     if (npix < 0 || !valid_dtype(x_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_match: bad npix / dtype");
     if (npix == 0) return QMRI_OK;
-    if (d->a0 != 0 || d->a1 != d->K)
+    if (d->a0 != 0 || d->a1 != d->K || d->shard_only)
         return qmri_fail(QMRI_EINVAL, "qmri_match on an atom-sharded handle: use qmri_match_keys_dev + a max-reduction + qmri_match_finish_dev");
     qmri_ctx* ctx = d->ctx;
     DevSetter ds(ctx->device);
@@ -1181,6 +1211,7 @@ extern "C" int qmri_synthesize(qmri_dict* d, const float* qmap, int64_t npix, fl
     if (!d || (npix > 0 && (!qmap || !X))) return qmri_fail(QMRI_EINVAL, "qmri_synthesize: null argument");
     if (npix < 0) return qmri_fail(QMRI_EINVAL, "npix < 0");
     if (d->Q < 2) return qmri_fail(QMRI_EINVAL, "qmri_synthesize needs dict.lut with (T1, T2) columns, got Q = %d", d->Q);
+    if (d->shard_only) return qmri_fail(QMRI_EINVAL, "qmri_synthesize needs the whole dictionary resident (handle holds atoms [%lld,%lld) only)", (long long)d->a0, (long long)d->a1);
     if (npix == 0) return QMRI_OK;
     qmri_ctx* ctx = d->ctx;
     DevSetter ds(ctx->device);
@@ -1206,4 +1237,203 @@ extern "C" int qmri_synthesize(qmri_dict* d, const float* qmap, int64_t npix, fl
     if (atom_index) QCUDA(cudaMemcpyAsync(atom_index, p.index, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     QCUDA(cudaStreamSynchronize(ctx->stream));
     return QMRI_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the bare sampling matrix: P.for / P.adj (setup_subsampling_spiralgrided.m:36-42, setup_subsampling_epi.m:31-35)
+// ------------------------------------------------------------------------------------------
+static int p_matrix(qmri_op* op, PMatrix* P) {
+    const size_t nm = std::max<size_t>((size_t)op->t.nmeas, 1);
+    if (!op->p_idx.p) {
+        QCHECK(op->p_idx.ensure(nm * sizeof(int32_t)));
+        QCHECK(op->p_fp.ensure((size_t)(op->L + 1) * sizeof(int)));
+        if (op->t.nmeas) QCUDA(cudaMemcpy(op->p_idx.p, op->t.idx.data(), (size_t)op->t.nmeas * sizeof(int32_t), cudaMemcpyHostToDevice));
+        QCUDA(cudaMemcpy(op->p_fp.p, op->t.frame_ptr.data(), (size_t)(op->L + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        if (!op->hV.empty()) {
+            QCHECK(op->p_V.ensure(op->hV.size() * sizeof(double)));
+            QCUDA(cudaMemcpy(op->p_V.p, op->hV.data(), op->hV.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    P->idx = op->p_idx.as<int32_t>();
+    P->frame_ptr = op->p_fp.as<int>();
+    P->V = op->hV.empty() ? nullptr : op->p_V.as<double>();
+    P->L = op->L;
+    P->C = op->C;
+    P->NM = (int64_t)op->N * op->M;
+    P->nmeas = op->t.nmeas;
+    return QMRI_OK;
+}
+
+extern "C" int qmri_op_for(qmri_op* op, const void* kvec, int k_dtype, void* y, int y_dtype) {
+    if (!op || !kvec || !y) return qmri_fail(QMRI_EINVAL, "qmri_op_for: null argument");
+    if (!valid_dtype(k_dtype) || !dtype_is_complex(y_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_op_for: bad dtype (y must be complex)");
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    PMatrix P;
+    QCHECK(p_matrix(op, &P));
+    const size_t n = op->plane(), nm = (size_t)op->t.nmeas;
+    QCHECK(op->p_k.ensure(2 * n * sizeof(double)));
+    QCHECK(op->p_y.ensure(2 * std::max<size_t>(nm, 1) * sizeof(double)));
+    QCHECK(op->p_stage.ensure(std::max(n * dtype_size(k_dtype), nm * dtype_size(y_dtype))));
+    double *kr = op->p_k.as<double>(), *ki = kr + n, *yr = op->p_y.as<double>(), *yi = yr + std::max<size_t>(nm, 1);
+    QCUDA(cudaMemcpyAsync(op->p_stage.p, kvec, n * dtype_size(k_dtype), cudaMemcpyHostToDevice, ctx->stream));
+    QCHECK(aux_unpack_f64(ctx, op->p_stage.p, k_dtype, kr, ki, n));
+    QCHECK(aux_p_for(ctx, P, kr, ki, yr, yi));
+    if (nm) {
+        QCHECK(aux_pack_f64(ctx, op->p_stage.p, y_dtype, yr, yi, nm));
+        QCUDA(cudaMemcpyAsync(y, op->p_stage.p, nm * dtype_size(y_dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    QCUDA(cudaStreamSynchronize(ctx->stream));
+    return QMRI_OK;
+}
+
+extern "C" int qmri_op_adj(qmri_op* op, const void* y, int y_dtype, void* kvec, int k_dtype) {
+    if (!op || !y || !kvec) return qmri_fail(QMRI_EINVAL, "qmri_op_adj: null argument");
+    if (!valid_dtype(y_dtype) || !dtype_is_complex(k_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_op_adj: bad dtype (the k-space vector must be complex)");
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    PMatrix P;
+    QCHECK(p_matrix(op, &P));
+    const size_t n = op->plane(), nm = (size_t)op->t.nmeas;
+    QCHECK(op->p_k.ensure(2 * n * sizeof(double)));
+    QCHECK(op->p_y.ensure(2 * std::max<size_t>(nm, 1) * sizeof(double)));
+    QCHECK(op->p_stage.ensure(std::max(n * dtype_size(k_dtype), nm * dtype_size(y_dtype))));
+    double *kr = op->p_k.as<double>(), *ki = kr + n, *yr = op->p_y.as<double>(), *yi = yr + std::max<size_t>(nm, 1);
+    if (nm) {
+        QCUDA(cudaMemcpyAsync(op->p_stage.p, y, nm * dtype_size(y_dtype), cudaMemcpyHostToDevice, ctx->stream));
+        QCHECK(aux_unpack_f64(ctx, op->p_stage.p, y_dtype, yr, yi, nm));
+    }
+    QCHECK(aux_p_adj(ctx, P, op->t.frame_ptr.data(), yr, yi, kr, ki));
+    QCHECK(aux_pack_f64(ctx, op->p_stage.p, k_dtype, kr, ki, n));
+    QCUDA(cudaMemcpyAsync(kvec, op->p_stage.p, n * dtype_size(k_dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    QCUDA(cudaStreamSynchronize(ctx->stream));
+    return QMRI_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// measurement noise (main_recon_tsmis_FFT.m:243)
+// ------------------------------------------------------------------------------------------
+extern "C" int qmri_awgn(qmri_ctx* ctx, void* y, int y_dtype, int64_t nmeas, int S, double snr_db, uint64_t seed) {
+    if (!ctx || (!y && nmeas > 0 && S > 0)) return qmri_fail(QMRI_EINVAL, "qmri_awgn: null argument");
+    if (!dtype_is_complex(y_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_awgn: measurements must be complex (QMRI_C64 / QMRI_C128)");
+    if (nmeas < 0 || S < 0) return qmri_fail(QMRI_EINVAL, "qmri_awgn: negative size");
+    if (nmeas == 0 || S == 0) return QMRI_OK;
+    DevSetter ds(ctx->device);
+    DevBuf raw, pw;
+    const size_t bytes = (size_t)nmeas * S * dtype_size(y_dtype);
+    int rc = raw.ensure(bytes);
+    if (!rc) rc = pw.ensure((size_t)S * sizeof(double));
+    auto body = [&]() -> int {
+        QCUDA(cudaMemcpyAsync(raw.p, y, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        QCHECK(aux_awgn(ctx, raw.p, y_dtype, nmeas, S, snr_db, seed, pw.as<double>()));
+        QCUDA(cudaMemcpyAsync(y, raw.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        QCUDA(cudaStreamSynchronize(ctx->stream));
+        return QMRI_OK;
+    };
+    if (!rc) rc = body();
+    raw.release();
+    pw.release();
+    return rc;
+}
+extern "C" int qmri_awgn_dev(qmri_ctx* ctx, float* y_dev, int64_t nmeas, int S, double snr_db, uint64_t seed, double* power_dev) {
+    if (!ctx || !y_dev || !power_dev) return qmri_fail(QMRI_EINVAL, "qmri_awgn_dev: null argument");
+    if (nmeas < 0 || S < 0) return qmri_fail(QMRI_EINVAL, "qmri_awgn_dev: negative size");
+    DevSetter ds(ctx->device);
+    return aux_awgn(ctx, y_dev, QMRI_C64, nmeas, S, snr_db, seed, power_dev);
+}
+
+// ------------------------------------------------------------------------------------------
+// foreground mask and metrics of the driver script (main_recon_tsmis_FFT.m:190-191, 328-384)
+// ------------------------------------------------------------------------------------------
+extern "C" int qmri_foreground_mask(qmri_ctx* ctx, const void* pd, int pd_dtype, int N, int M, double thresh, float* mask) {
+    if (!ctx || !pd || !mask) return qmri_fail(QMRI_EINVAL, "qmri_foreground_mask: null argument");
+    if (N < 1 || M < 1 || !valid_dtype(pd_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_foreground_mask: bad size / dtype");
+    DevSetter ds(ctx->device);
+    const size_t n = (size_t)N * M;
+    DevBuf raw, pl, sc;
+    int rc = raw.ensure(n * 16);
+    if (!rc) rc = pl.ensure(4 * n * sizeof(double));  // re, im, |pd|, mask
+    if (!rc) rc = sc.ensure(2 * n);
+    auto body = [&]() -> int {
+        double *re = pl.as<double>(), *im = re + n, *ab = im + n, *mk = ab + n;
+        QCUDA(cudaMemcpyAsync(raw.p, pd, n * dtype_size(pd_dtype), cudaMemcpyHostToDevice, ctx->stream));
+        QCHECK(aux_unpack_f64(ctx, raw.p, pd_dtype, re, im, n));
+        QCHECK(aux_abs_scale(ctx, re, dtype_is_complex(pd_dtype) ? im : nullptr, nullptr, nullptr, ab, n));
+        QCHECK(aux_foreground_mask(ctx, ab, N, M, thresh, mk, sc.as<unsigned char>()));
+        QCHECK(aux_pack_f64(ctx, raw.p, QMRI_F32, mk, nullptr, n));
+        QCUDA(cudaMemcpyAsync(mask, raw.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        QCUDA(cudaStreamSynchronize(ctx->stream));
+        return QMRI_OK;
+    };
+    if (!rc) rc = body();
+    raw.release(); pl.release(); sc.release();
+    return rc;
+}
+
+extern "C" int qmri_recon_metrics(qmri_ctx* ctx, int N, int M, int C, const void* qmap, int qmap_dtype, const void* qmap0, int qmap0_dtype,
+                                  const float* mask, const void* X, int x_dtype, const void* X0, int x0_dtype, double* out) {
+    if (!ctx || !qmap || !qmap0 || !out) return qmri_fail(QMRI_EINVAL, "qmri_recon_metrics: null argument");
+    if ((X == nullptr) != (X0 == nullptr)) return qmri_fail(QMRI_EINVAL, "qmri_recon_metrics: pass both X and X0 or neither");
+    if (N < 1 || M < 1 || C < 0 || C > 1000 || !valid_dtype(qmap_dtype) || !valid_dtype(qmap0_dtype) || (X && (!valid_dtype(x_dtype) || !valid_dtype(x0_dtype))))
+        return qmri_fail(QMRI_EINVAL, "qmri_recon_metrics: bad size / dtype");
+    DevSetter ds(ctx->device);
+    const size_t n = (size_t)N * M;
+    const int nch = X ? C : 0, npairs = 3 + nch;
+    const size_t big = std::max<size_t>(3, (size_t)nch) * n;
+    DevBuf raw, wk, pa, pb, part, res;
+    int rc = raw.ensure(big * 16);
+    if (!rc) rc = wk.ensure((2 * big + n + 2) * sizeof(double));  // re, im planes of the array being converted, mask, two maxima
+    if (!rc) rc = pa.ensure((size_t)npairs * n * sizeof(double));
+    if (!rc) rc = pb.ensure((size_t)npairs * n * sizeof(double));
+    if (!rc) rc = part.ensure(aux_pair_metrics_partial_elems(npairs, N, M) * sizeof(double));
+    if (!rc) rc = res.ensure((size_t)npairs * 3 * sizeof(double));
+    auto body = [&]() -> int {
+        double *re = wk.as<double>(), *im = re + big, *mk = im + big, *mx = mk + n;
+        double *A = pa.as<double>(), *B = pb.as<double>();
+        const double* mkp = nullptr;
+        if (mask) {
+            QCUDA(cudaMemcpyAsync(raw.p, mask, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            QCHECK(aux_unpack_f64(ctx, raw.p, QMRI_F32, mk, nullptr, n));
+            mkp = mk;
+        }
+        // side 0 = estimate (qmap, X), side 1 = reference (qmap0, X0)
+        for (int side = 0; side < 2; ++side) {
+            const void* q = side ? qmap0 : qmap;
+            const int qd = side ? qmap0_dtype : qmap_dtype;
+            double* dst = side ? B : A;
+            QCUDA(cudaMemcpyAsync(raw.p, q, 3 * n * dtype_size(qd), cudaMemcpyHostToDevice, ctx->stream));
+            QCHECK(aux_unpack_f64(ctx, raw.p, qd, re, im, 3 * n));
+            // t1 = qmap(:,:,1) .* mask, t2 likewise (:330-333): MAE / PSNR / SSIM compare the real parts
+            QCUDA(cudaMemcpyAsync(dst, re, 2 * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (mkp) QCHECK(aux_mul_mask(ctx, dst, mkp, n, 2));
+            // pd = |qmap(:,:,3) .* mask| / max(|.|)  (:334-337)
+            QCHECK(aux_abs_scale(ctx, re + 2 * n, dtype_is_complex(qd) ? im + 2 * n : nullptr, mkp, nullptr, dst + 2 * n, n));
+            QCHECK(aux_absmax(ctx, dst + 2 * n, n, mx + side));
+            QCHECK(aux_abs_scale(ctx, dst + 2 * n, nullptr, nullptr, mx + side, dst + 2 * n, n));
+            if (nch) {  // psnr / ssim of abs(X(:,:,c)) against abs(X0(:,:,c)), no mask (:355-369)
+                const void* x = side ? X0 : X;
+                const int xd = side ? x0_dtype : x_dtype;
+                QCUDA(cudaMemcpyAsync(raw.p, x, (size_t)nch * n * dtype_size(xd), cudaMemcpyHostToDevice, ctx->stream));
+                QCHECK(aux_unpack_f64(ctx, raw.p, xd, re, im, (size_t)nch * n));
+                QCHECK(aux_abs_scale(ctx, re, dtype_is_complex(xd) ? im : nullptr, nullptr, nullptr, dst + 3 * n, (size_t)nch * n));
+            }
+        }
+        QCHECK(aux_pair_metrics(ctx, A, B, mkp, npairs, N, M, part.as<double>(), res.as<double>()));
+        std::vector<double> h((size_t)npairs * 3);
+        QCUDA(cudaMemcpyAsync(h.data(), res.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        QCUDA(cudaStreamSynchronize(ctx->stream));
+        // out: tsmi_mean_psnr, tsmi_mean_ssim, t1_{mae,psnr,ssim}, t2_{...}, pd_{...}  (the script's print order, :372-379)
+        double ps = 0.0, ss = 0.0;
+        for (int c = 0; c < nch; ++c) {
+            ps += h[(size_t)(3 + c) * 3 + 1];
+            ss += h[(size_t)(3 + c) * 3 + 2];
+        }
+        out[0] = nch ? ps / nch : NAN;
+        out[1] = nch ? ss / nch : NAN;
+        for (int k = 0; k < 9; ++k) out[2 + k] = h[k];
+        return QMRI_OK;
+    };
+    if (!rc) rc = body();
+    raw.release(); wk.release(); pa.release(); pb.release(); part.release(); res.release();
+    return rc;
 }

@@ -246,7 +246,8 @@ static int launch_mc(qmri_ctx* ctx, const K1Params& p, int S, int ns_max) {
     using Cfg = K1Cfg<MC>;
     static_assert(Cfg::THREADS / MC == K1_PHASES, "one work list per row phase");
     size_t smem = (size_t)(MC * CS + NF + TWP + ns_max + 1) * sizeof(float2) + (size_t)K1_PHASES * p.p4_len * 4 + (size_t)ns_max * 2 + 16;
-    static size_t configured = 0;  // the table sizes depend on the operator: raise the limit when a larger one comes along
+    static size_t configured_dev[QMRI_MAX_DEV] = {};  // the table sizes depend on the operator: raise the limit when a larger one comes along
+    size_t& configured = configured_dev[qmri_dev_slot(ctx)];
     if (smem > configured) {
         QCUDA(cudaFuncSetAttribute(xupdate_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

@@ -294,7 +294,8 @@ size_t adj_smem(const K1Params& p) {
 
 template <int MODE>
 int launch_mode(qmri_ctx* ctx, const K1Params& p, int S) {
-    static size_t conf_f = 0, conf_a = 0;
+    static size_t conf_f_dev[QMRI_MAX_DEV] = {}, conf_a_dev[QMRI_MAX_DEV] = {};
+    size_t &conf_f = conf_f_dev[qmri_dev_slot(ctx)], &conf_a = conf_a_dev[qmri_dev_slot(ctx)];
     const size_t sf = fwd_smem(p), sa = adj_smem(p);
     if (sf > conf_f) {
         QCUDA(cudaFuncSetAttribute(stream_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));

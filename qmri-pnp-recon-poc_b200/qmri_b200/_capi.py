@@ -74,12 +74,19 @@ SIGNATURES = {
     "qmri_admm_destroy": (_i, [_vp]),
     "qmri_admm_xupdate_only": (_i, [_vp, _i]),
     "qmri_dict_load": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _pp]),
+    "qmri_dict_load_shard": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _pp]),
     "qmri_dict_destroy": (_i, [_vp]),
     "qmri_match": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "qmri_match_dev": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "qmri_match_keys_dev": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "qmri_match_finish_dev": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "qmri_synthesize": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "qmri_op_for": (_i, [_vp, _vp, _i, _vp, _i]),
+    "qmri_op_adj": (_i, [_vp, _vp, _i, _vp, _i]),
+    "qmri_awgn": (_i, [_vp, _vp, _i, _i64, _i, _d, C.c_uint64]),
+    "qmri_awgn_dev": (_i, [_vp, _vp, _i64, _i, _d, C.c_uint64, _vp]),
+    "qmri_foreground_mask": (_i, [_vp, _vp, _i, _i, _i, _d, _vp]),
+    "qmri_recon_metrics": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
 }
 
 _lib = None

@@ -79,6 +79,14 @@ class UNetRes:
         sd, in_nc = load_checkpoint_state_dict(path_or_obj)
         return cls(sd, in_nc=in_nc, ctx=ctx)
 
+    @classmethod
+    def from_onnx(cls, path_or_bytes, ctx=None):
+        """Import of the reference's ONNX export (``utils.py:444-485``; ``importONNXNetwork`` at
+        ``main_recon_tsmis_FFT.m:138-152``): the graph's initializers are the weights - see ``onnx_import``."""
+        from .onnx_import import load_onnx_state_dict
+        sd, in_nc = load_onnx_state_dict(path_or_bytes)
+        return cls(sd, in_nc=in_nc, ctx=ctx)
+
     def __init__(self, state_dict, in_nc=10, ctx=None):
         self.ctx = ctx or Context.default()
         self.in_nc = int(in_nc)

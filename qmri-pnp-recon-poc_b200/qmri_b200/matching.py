@@ -24,7 +24,9 @@ from ._capi import Context, as_f, check, dtype_code, ptr
 class Dictionary:
     """Device-resident ``dict`` (qmri_dict).  ``shard`` = (begin, end) atom range scored here."""
 
-    def __init__(self, dict_, ctx=None, shard=None):
+    def __init__(self, dict_, ctx=None, shard=None, shard_only=False):
+        """``shard_only=True``: ``dict_['D']`` holds ONLY the atoms ``[shard[0], shard[1])`` (``normD`` / ``lut`` stay whole,
+        12 B per atom) - per-rank memory and upload time scale with K / world (``qmri_dict_load_shard``)."""
         self.ctx = ctx or Context.default()
         D = np.asfortranarray(np.asarray(dict_["D"]))
         if np.iscomplexobj(D):
@@ -36,6 +38,13 @@ class Dictionary:
             raise ValueError("dict.D must be K x C")
         self.K, self.C = D.shape
         normD = np.ascontiguousarray(np.asarray(dict_["normD"], dtype=np.float32).reshape(-1))
+        self.shard_only = bool(shard_only)
+        if self.shard_only:
+            if shard is None:
+                raise ValueError("shard_only needs shard=(begin, end)")
+            if D.shape[0] != int(shard[1]) - int(shard[0]):
+                raise ValueError(f"shard_only: dict.D must hold the {int(shard[1]) - int(shard[0])} atoms of the shard, got {D.shape[0]} rows")
+            self.K = normD.size
         lut = np.asfortranarray(np.asarray(dict_["lut"], dtype=np.float32))
         if lut.ndim != 2 or lut.shape[0] != self.K or normD.size != self.K:
             raise ValueError("dict.lut must be K x Q and dict.normD must have K entries")
@@ -43,8 +52,8 @@ class Dictionary:
         self.host_D, self.host_normD = D, normD
         self.shard = (0, self.K) if shard is None else (int(shard[0]), int(shard[1]))
         h = C.c_void_p()
-        check(self.ctx.lib.qmri_dict_load(self.ctx.handle, ptr(D), ptr(normD), ptr(lut), self.K, self.C, self.Q,
-                                          self.shard[0], self.shard[1], C.byref(h)))
+        load = self.ctx.lib.qmri_dict_load_shard if self.shard_only else self.ctx.lib.qmri_dict_load
+        check(load(self.ctx.handle, ptr(D), ptr(normD), ptr(lut), self.K, self.C, self.Q, self.shard[0], self.shard[1], C.byref(h)))
         self.handle = h
 
     def close(self):

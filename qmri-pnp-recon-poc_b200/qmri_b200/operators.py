@@ -39,6 +39,33 @@ class SubsamplingPattern:
         check(self.ctx.lib.qmri_op_indices(self.handle, ptr(idx), ptr(fp)))
         return idx, fp
 
+    # P.for / P.adj, the handles the reference constructors return (setup_subsampling_spiralgrided.m:41-42,
+    # setup_subsampling_epi.m:34-35).  `for` is a Python keyword: the forward handle is `P.for_` (also P["for"] / P["adj"]).
+    def for_(self, vec):
+        """``y = P.for(vec)``: ``vec`` = the N*M*C k-space column ``reshape(fft2(x),[],1)`` -> ``nmeas`` samples."""
+        v = as_f(np.asarray(vec).reshape(-1, order="F"))
+        if v.size != self.N * self.M * self.C:
+            raise ValueError(f"P.for expects {self.N * self.M * self.C} entries, got {v.size}")
+        y = np.zeros(self.nmeas, np.complex64 if v.dtype in (np.float32, np.complex64) else np.complex128)
+        check(self.ctx.lib.qmri_op_for(self.handle, ptr(v), dtype_code(v), ptr(y), dtype_code(y)))
+        return y
+
+    def adj(self, y):
+        """``vec = P.adj(y)`` = ``P' * y``: ``nmeas`` samples -> the N*M*C k-space column."""
+        y = as_f(np.asarray(y).reshape(-1, order="F"))
+        if y.size != self.nmeas:
+            raise ValueError(f"P.adj expects {self.nmeas} entries, got {y.size}")
+        v = np.zeros(self.N * self.M * self.C, np.complex64 if y.dtype in (np.float32, np.complex64) else np.complex128)
+        check(self.ctx.lib.qmri_op_adj(self.handle, ptr(y), dtype_code(y), ptr(v), dtype_code(v)))
+        return v
+
+    def __getitem__(self, name):
+        if name == "for":
+            return self.for_
+        if name == "adj":
+            return self.adj
+        raise KeyError(name)
+
     def close(self):
         if self.handle:
             self.ctx.lib.qmri_op_destroy(self.handle)
@@ -152,3 +179,23 @@ class FOperator:
 
 def fft_operator(P):
     return FOperator(P)
+
+
+def awgn(Y, snr, mode="measured", seed=0, ctx=None):
+    """``Y = awgn(Y, snr, 'measured')`` (``main_recon_tsmis_FFT.m:243``) on the GPU: complex white Gaussian noise of power
+    ``mean(|Y|^2) / 10^(snr/10)``, per slice (column) of ``Y``.  Philox-4x32-10 keyed by ``seed``: reproducible, but not
+    MATLAB's random stream (statistical equality only)."""
+    if mode != "measured":
+        raise ValueError("only awgn(Y, snr, 'measured') is used by the reference (main_recon_tsmis_FFT.m:243)")
+    ctx = ctx or Context.default()
+    Y = np.array(Y, order="F", copy=True)
+    if not np.iscomplexobj(Y):
+        Y = Y.astype(np.complex128)
+    if Y.dtype not in (np.complex64, np.complex128):
+        Y = Y.astype(np.complex128)
+    if Y.ndim not in (1, 2):
+        raise ValueError("Y must be nmeas or nmeas x S")
+    nmeas = Y.shape[0]
+    S = Y.shape[1] if Y.ndim == 2 else 1
+    check(ctx.lib.qmri_awgn(ctx.handle, ptr(Y), dtype_code(Y), nmeas, S, float(snr), int(seed) & 0xFFFFFFFFFFFFFFFF))
+    return Y

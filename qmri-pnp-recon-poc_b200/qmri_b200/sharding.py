@@ -67,31 +67,47 @@ def allreduce_keys(keys, group=None):
     return keys
 
 
-def mrf_dtm_sharded(dictionary, x_re, x_im, npix, group=None, want_mt=False, want_dm=True):
+def mrf_dtm_sharded(dictionary, x_re, x_im, npix, group=None, want_mt=False, want_dm=True, shared_stream=False):
     """Atom-sharded ``mrf_dtm_cpu`` on device tensors.
 
-    ``dictionary``: a ``Dictionary`` created with ``shard=atom_shard(K, world, rank)`` (the full LUT / normD is resident on
-    every rank, only the scoring is sharded); ``x_re`` / ``x_im``: planar fp32 torch CUDA tensors ``[C][npix]``
-    (``x_im`` may be None for real data).  Returns torch CUDA tensors ``qmap [Q][npix]``, ``pd [npix][2]``, ``mt``, ``dm``.
+    ``dictionary``: a ``Dictionary`` created with ``shard=atom_shard(K, world, rank)``; with ``shard_only=True`` only the shard's
+    atoms are resident on this rank (LUT / normD are replicated: 12 B per atom).  ``x_re`` / ``x_im``: planar fp32 torch CUDA
+    tensors ``[C][npix]`` (``x_im`` may be None for real data).  Returns torch CUDA tensors ``qmap [Q][npix]``,
+    ``pd [npix][2]``, ``mt``, ``dm``.
+
+    Exchange: one max all-reduce of the packed keys (8 B per pixel).  With a shard-only dictionary the owner of each pixel's
+    winning atom computes its outputs (zeros elsewhere) and one sum all-reduce over the packed outputs (``(Q + 4)`` x 4 B per
+    pixel) gives every rank the result - exact, since every pixel has exactly one non-zero contribution.
+    ``shared_stream=True``: the library context launches on torch's current stream (``ctx.set_stream``), so kernels and
+    collectives are ordered by the stream and no host synchronisation is needed.
     """
     import torch
     d = dictionary
     dev = x_re.device
     lib = d.ctx.lib
+    sync_t = (lambda: None) if shared_stream else (lambda: torch.cuda.synchronize(dev))
+    sync_l = (lambda: None) if shared_stream else d.ctx.synchronize
     keys = torch.zeros(npix, dtype=torch.int64, device=dev)
     pim = C.c_void_p(x_im.data_ptr()) if x_im is not None else None
-    torch.cuda.synchronize(dev)  # x was produced on torch's stream; the library launches on its own
+    sync_t()  # x was produced on torch's stream; the library launches on its own unless the stream is shared
     check(lib.qmri_match_keys_dev(d.handle, C.c_void_p(x_re.data_ptr()), pim, npix, C.c_void_p(keys.data_ptr())))
-    d.ctx.synchronize()
-    allreduce_keys(keys, group)  # the only exchange: 8 B per pixel
-    torch.cuda.synchronize(dev)
-    qmap = torch.empty(d.Q * npix, dtype=torch.float32, device=dev)
-    pd = torch.empty(2 * npix, dtype=torch.float32, device=dev)
-    mt = torch.empty(npix, dtype=torch.float32, device=dev) if want_mt else None
-    dm = torch.empty(npix, dtype=torch.int32, device=dev) if want_dm else None
+    sync_l()
+    allreduce_keys(keys, group)  # 8 B per pixel
+    sync_t()
+    # one packed output buffer: [qmap Q | pd 2 | mt 1 | dm 1] planes of npix (dm as int32 bits)
+    Q = d.Q
+    out = torch.empty((Q + 4) * npix, dtype=torch.float32, device=dev)
+    qmap, pd = out[:Q * npix], out[Q * npix:(Q + 2) * npix]
+    mt, dm = out[(Q + 2) * npix:(Q + 3) * npix], out[(Q + 3) * npix:].view(torch.int32)
     check(lib.qmri_match_finish_dev(d.handle, C.c_void_p(x_re.data_ptr()), pim, npix, C.c_void_p(keys.data_ptr()),
                                     C.c_void_p(qmap.data_ptr()), C.c_void_p(pd.data_ptr()),
-                                    C.c_void_p(mt.data_ptr()) if mt is not None else None,
-                                    C.c_void_p(dm.data_ptr()) if dm is not None else None))
-    d.ctx.synchronize()
-    return qmap.view(d.Q, npix), pd.view(npix, 2), mt, dm
+                                    C.c_void_p(mt.data_ptr()), C.c_void_p(dm.data_ptr())))
+    sync_l()
+    if getattr(d, "shard_only", False):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            # dm travels as int32: summing the owner's index with zeros is exact
+            dist.all_reduce(out[:(Q + 3) * npix], op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(dm, op=dist.ReduceOp.SUM, group=group)
+            sync_t()
+    return qmap.view(Q, npix), pd.view(npix, 2), (mt if want_mt else None), (dm if want_dm else None)
