@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "match_kernel.h"
+#include "match_score.cuh"
 
 namespace {
 
@@ -28,17 +29,6 @@ constexpr int K2_THREADS = 256;
 constexpr int K2_CHUNK = 512;  // atoms per shared-memory stage
 constexpr int K2_GROUP = 16;   // atoms per (max, index) bookkeeping step
 
-// |<d, x>|^2 with a fixed operation order (the rescan must reproduce the main loop bit for bit)
-template <int C, bool CPLX>
-__device__ __forceinline__ float k2_score(const float* d, const float* xr, const float* xi) {
-    float sr = 0.f, si = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        sr = fmaf(d[c], xr[c], sr);
-        if (CPLX) si = fmaf(d[c], xi[c], si);
-    }
-    return CPLX ? fmaf(si, si, sr * sr) : sr * sr;
-}
 
 template <int C, int CP, int PX, bool CPLX>
 __global__ void __launch_bounds__(K2_THREADS) match_kernel(K2Params p) {

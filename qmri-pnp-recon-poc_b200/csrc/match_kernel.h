@@ -51,3 +51,15 @@ struct K4Params {
     int32_t* index;      // optional [npix], 1-based nearest atom
 };
 int k4_launch(qmri_ctx* ctx, const K4Params& p);
+
+// K2, tensor-pipe variant (match_tc.cu): atoms [a0, a1) packed as tf32-split K-major rows + their TMA descriptor
+struct K2TcDict {
+    float* Dt = nullptr;   // [ntiles * 128][32]
+    int ntiles = 0;
+    alignas(64) unsigned char mapB[128];
+};
+bool k2tc_supported(int C);
+int k2tc_dict_build(qmri_ctx* ctx, const float* D, int64_t ldD, int64_t row0, int C, int64_t a0, int64_t a1, K2TcDict* out);
+void k2tc_dict_free(K2TcDict* d);
+size_t k2tc_stage_elems(int64_t npix);
+int k2tc_launch_keys(qmri_ctx* ctx, const K2TcDict& d, const K2Params& p, float* stage);

@@ -1088,6 +1088,9 @@ struct qmri_dict {
     float* Dp_alloc = nullptr;  // what cudaMalloc returned; Dp = Dp_alloc - a0 * CP when only the shard's atoms are resident
     bool shard_only = false;    // D holds atoms [a0, a1) only: finish writes the pixels whose winner this handle owns, zeros elsewhere
     DevBuf stage, x_re, x_im, keys, qmap, pd, mt, dm;
+    K2TcDict tc;          // tensor-pipe packing of the scored atoms (empty when C > 10 or the descriptor API is missing)
+    bool tc_ok = false;
+    DevBuf tc_stage;      // tf32-split pixel rows of the current call
 };
 
 static int dict_load(qmri_ctx* ctx, const float* D, const float* normD, const float* lut, int64_t K, int C, int Q,
@@ -1123,6 +1126,14 @@ static int dict_load(qmri_ctx* ctx, const float* D, const float* normD, const fl
         qmri_dict_destroy(d);
         return qmri_fail(QMRI_ECUDA, "dictionary upload failed: %s", cudaGetErrorString(e));
     }
+    if (k2tc_supported(C)) {
+        int rt = k2tc_dict_build(ctx, D, R, shard_only ? shard_begin : 0, C, shard_begin, shard_end, &d->tc);
+        if (rt) {
+            qmri_dict_destroy(d);
+            return rt;
+        }
+        d->tc_ok = true;
+    }
     *out = d;
     return QMRI_OK;
 }
@@ -1139,6 +1150,8 @@ extern "C" int qmri_dict_destroy(qmri_dict* d) {
     DevSetter ds(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
     cudaFree(d->Dp_alloc); cudaFree(d->normD); cudaFree(d->lut);
+    k2tc_dict_free(&d->tc);
+    d->tc_stage.release();
     d->stage.release(); d->x_re.release(); d->x_im.release(); d->keys.release();
     d->qmap.release(); d->pd.release(); d->mt.release(); d->dm.release();
     delete d;
@@ -1154,6 +1167,19 @@ extern "C" int qmri_match_keys_dev(qmri_dict* d, const float* x_re, const float*
     K2Params p = {};
     p.x_re = x_re; p.x_im = x_im; p.npix = npix; p.Dp = d->Dp; p.a0 = d->a0; p.a1 = d->a1;
     p.keys = (unsigned long long*)keys_dev; p.C = d->C; p.CP = d->CP;
+    // Pipe choice (profiles/r02_k2_pipes.md): the tcgen05 tf32 kernel from ~2000 atoms on, the FP32-FMA kernel for small
+    // ranges and for C > 10; QMRI_K2_PIPE=fma|tensor forces one (tests, profiling).  Both produce the same keys.
+    const char* pipe = getenv("QMRI_K2_PIPE");
+    bool tensor = d->tc_ok && (d->a1 - d->a0) >= 2048;
+    if (pipe && !strcmp(pipe, "fma")) tensor = false;
+    if (pipe && !strcmp(pipe, "tensor")) {
+        if (!d->tc_ok) return qmri_fail(QMRI_EUNSUPPORTED, "QMRI_K2_PIPE=tensor: this dictionary (C = %d) has no tensor-pipe packing", d->C);
+        tensor = true;
+    }
+    if (tensor) {
+        QCHECK(d->tc_stage.ensure(k2tc_stage_elems(npix) * sizeof(float)));
+        return k2tc_launch_keys(d->ctx, d->tc, p, d->tc_stage.as<float>());
+    }
     return k2_launch_keys(d->ctx, p);
 }
 extern "C" int qmri_match_finish_dev(qmri_dict* d, const float* x_re, const float* x_im, int64_t npix, const uint64_t* keys_dev,
