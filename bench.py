@@ -256,9 +256,45 @@ class FastFOperator:
         return sfft.ifft2(k, axes=(0, 1), workers=self.workers) * np.sqrt(self.N * self.M)
 
 
+REF_ENVS = {"inherited": {}, "omp1": {"OMP_NUM_THREADS": "1"}, "omp1_passive": {"OMP_NUM_THREADS": "1", "OMP_WAIT_POLICY": "PASSIVE"}}
+
+
+def pick_reference_env(args):
+    """The CPU arm's speed depends on how the OpenMP runtimes of NumPy / SciPy / PyTorch share the cores (measured on the B200
+    hosts: the same code ran 4.2 it/s with the inherited environment and 8 it/s under torchrun's OMP_NUM_THREADS=1, which stops
+    the second runtime's spinning pool from oversubscribing; on other hosts it is the other way round).  Environment variables
+    must be set before the libraries load, so each candidate is probed in a child process (two iterations) and the fastest is
+    used for the measurement - the reference arm gets the best configuration the box offers."""
+    best, best_name = None, "inherited"
+    for name, env in REF_ENVS.items():
+        e = dict(os.environ, QMRI_REF_CHILD=name, **env)
+        if name == "inherited":
+            e = dict(os.environ, QMRI_REF_CHILD=name)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-probe", "--mask", args.mask, "--atoms", "2000", "--cut", str(args.cut)]
+        try:
+            out = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600)
+            t = float(out.stdout.strip().splitlines()[-1])
+        except Exception:
+            continue
+        sys.stderr.write(f"[bench] reference environment {name}: {1e3 * t:.1f} ms per ADMM iteration\n")
+        if best is None or t < best:
+            best, best_name = t, name
+    return best_name
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return  # the other ranks exit 0 without work
+    if args.ref_probe:   # child of pick_reference_env: seconds per ADMM iteration with tuned thread counts
+        ref = CpuReference(args)
+        ref.tune()
+        print(ref.iterations(2) / 2)
+        return
+    if "QMRI_REF_CHILD" not in os.environ:
+        name = pick_reference_env(args)
+        env = dict(os.environ, QMRI_REF_CHILD=name, **REF_ENVS[name])
+        sys.stdout.flush()
+        os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env)
     ref = CpuReference(args)
     threads = ref.tune()   # untimed: also warms oneDNN primitives / FFT plans
     for _ in range(max(0, args.warmup - 1)):
@@ -276,7 +312,8 @@ def run_reference(args, rank, world):
               f"{args.atoms} atoms, extrapolated to the job (per slice: {args.iters} iterations + {HW} pixels); measured "
               f"{1e3 * np.mean([t[1] for t in times]):.1f} ms per iteration, {1e9 * np.mean([t[2] for t in times]) / args.atoms:.3f} ns per px-atom; "
               f"oracle/ restatement (scipy.fft x-update + PyTorch-CPU UNetRes + sgemm matching), {threads} threads of {ref.ncpu} "
-              f"(tuned); MATLAB / Octave absent from the image; N > 1: rank 0 alone runs this CPU job")
+              f"(tuned), OpenMP environment '{os.environ.get('QMRI_REF_CHILD', 'inherited')}' (fastest of {list(REF_ENVS)}); MATLAB / Octave absent "
+              f"from the image; N > 1: rank 0 alone runs this CPU job")
     line = {
         "metric": METRIC, "value": value, "unit": "slice-iterations/s", "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
@@ -520,13 +557,16 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        ref = CpuReference(args)
-        threads = ref.tune()
-        per_it, t_it, t_px = ref.sample(args.cpu_iters, args.ref_match_px)
-        cpu = {"value": 1.0 / per_it, "unit": "slice-iterations/s", "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_iters} ADMM iterations of one slice ({1e3 * t_it:.1f} ms each) + matching of {args.ref_match_px} pixels against "
-                         f"{args.atoms} atoms ({1e9 * t_px / args.atoms:.3f} ns per px-atom), extrapolated to the job; oracle/ restatement, "
-                         f"{threads} of {ref.ncpu} threads; MATLAB / Octave absent"}
+        # the reference arm as a child process (it picks its own OpenMP environment): one step of its bounded sample
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1", "--mask", args.mask, "--cut", str(args.cut),
+               "--atoms", str(args.atoms), "--slices", str(args.slices), "--iters", str(args.iters), "--ref-iters", str(args.cpu_iters),
+               "--ref-match-px", str(args.ref_match_px)]
+        try:
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+            out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1200)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:  # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": "slice-iterations/s", "cores": os.cpu_count(), "kind": "port", "sample": f"reference arm failed: {e}"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "slice-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -634,6 +674,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=8)
     ap.add_argument("--ref-iters", type=int, default=3)
     ap.add_argument("--ref-match-px", type=int, default=2048)
+    ap.add_argument("--ref-probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--clock-period", type=float, default=2.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extra", action="store_true")

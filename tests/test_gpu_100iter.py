@@ -3,13 +3,10 @@ built-in random-init UNetRes in tensor mode (split-bf16 tcgen05) through the CUD
 and a 15-slice batch - relative L2 against ``oracle.admm.pnp_admm`` (float64 x-update + PyTorch-CPU fp32 UNetRes) recorded every
 10 iterations.
 
-What is asserted, and why it is not simply "1e-4 at iteration 100": the random-init DRUNet is NOT a contraction, so the ADMM
-map amplifies any perturbation from iteration to iteration; two correct fp32 implementations of the same loop (this library's
-fp32 CUDA-core mode vs the PyTorch CPU forward: 5e-7 apart per forward) drift apart at the same rate as the tensor mode does.
-The test therefore asserts (a) <= 1e-4 for the first 10 iterations (the per-iteration parity bar, before amplification
-dominates), (b) that tensor-mode drift at iteration 100 stays within DRIFT_FACTOR x the drift of the fp32 exact mode (i.e. the
-tensor path adds no error mechanism of its own), and records the whole curve in gpurun_out/drift100.json (copied to
-profiles/ by the builder)."""
+Measured on B200 (profiles/r02_drift100.json): the loop does not amplify the per-forward difference - tensor mode stays at
+1e-6 (EPI) / 2e-5 (spiral) relative L2 through all 100 iterations, the fp32 CUDA-core mode at 1e-7 ... 1e-5; asserted here:
+<= 1e-4 at EVERY checkpoint (the north-star denoiser tolerance, which bounds the loop), both precision modes, and the curve is
+written to gpurun_out/drift100.json."""
 import json
 import os
 import time
@@ -22,7 +19,6 @@ from conftest import ROOT, rel_l2
 pytestmark = pytest.mark.gpu
 
 CHECKPOINTS = list(range(10, 101, 10))
-DRIFT_FACTOR = 30.0
 
 
 def _problem(q, kind, S, seed):
@@ -86,6 +82,6 @@ def test_100_iterations_against_the_oracle(kind, S, picks):
     print(json.dumps(res))
     for s in picks:
         tc, fp = res["tc"][str(s)], res["fp32"][str(s)]
-        assert tc[0] <= 1e-4 and fp[0] <= 1e-4, f"{kind} S={S} slice {s}: iteration 10 drift tc {tc[0]:.2e} fp32 {fp[0]:.2e}"
         assert np.all(np.isfinite(tc)) and np.all(np.isfinite(fp))
-        assert tc[-1] <= DRIFT_FACTOR * max(fp[-1], 1e-6), f"{kind} S={S} slice {s}: tensor-mode drift {tc[-1]:.2e} vs fp32-mode drift {fp[-1]:.2e}"
+        assert max(tc) <= 1e-4, f"{kind} S={S} slice {s}: tensor-mode drift {tc}"
+        assert max(fp) <= 1e-4, f"{kind} S={S} slice {s}: fp32-mode drift {fp}"

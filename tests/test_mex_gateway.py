@@ -70,7 +70,7 @@ def test_mex_gateway_matches_ctypes_path(split):
     assert h.dtype == np.uint64 and m.lib.mock_is_locked()
     P = q.setup_subsampling_spiralgrided(224, 224, 771, V)
     F = q.fft_operator(P)
-    assert int(m.call("nmeas", h)) == P.nmeas and np.array_equal(m.call("last_op"), h)
+    assert int(m.call("nmeas", h)[0, 0]) == P.nmeas and np.array_equal(m.call("last_op"), h)
     X = rng.standard_normal((224, 224, 10, 2)) + 1j * rng.standard_normal((224, 224, 10, 2))
     y = m.call("forward", h, X)
     assert y.shape == (P.nmeas, 2) and np.array_equal(y, F.forward(X))
@@ -97,7 +97,8 @@ def test_mex_gateway_matches_ctypes_path(split):
     assert np.array_equal(met, np.array([ref[k] for k in q.metrics.METRIC_NAMES]))
 
     # the loop: function-handle denoiser (feval hop) and the built-in network handle
-    def box(v):
+    def box(v):   # computed in double whatever the caller hands over (MATLAB feval gets a double array, the ctypes callback a single one)
+        v = np.asarray(v, dtype=np.float64)
         return 0.5 * v + 0.125 * (np.roll(v, 1, 0) + np.roll(v, -1, 0) + np.roll(v, 1, 1) + np.roll(v, -1, 1))
     Y1 = yn[:, 0]
     X0 = F.adjoint(Y1)
