@@ -236,6 +236,23 @@ int qmri_foreground_mask(qmri_ctx* ctx, const void* pd, int pd_dtype, int N, int
 int qmri_recon_metrics(qmri_ctx* ctx, int N, int M, int C, const void* qmap, int qmap_dtype, const void* qmap0, int qmap0_dtype,
                        const float* mask, const void* X, int x_dtype, const void* X0, int x0_dtype, double* out);
 
+/* ---- LRTV comparison baseline ------------------------------------------
+ * x = FISTA_deep(data, param)   main_files/algorithms/LRTV/FISTA_deep.m:1-115 with the TV prox of
+ * unlocbox/prox/prox_tv.m (called at main_recon_tsmis_FFT.m:272-282: K = 4e-5, iter = 200, step = numel(X0)/numel(Y),
+ * tol = 1e-4, backtrack = 1).  One slice; y nmeas complex -> x N x M x C complex.  The TV prox keeps the toolbox defaults
+ * (tv_tol = 10e-4, tv_maxit = 200) unless set.  Double-precision state on the device, the operator in single. */
+typedef struct qmri_lrtv_params {
+    double K;        /* param.K: TV weight                               */
+    int iters;       /* param.iter                                       */
+    double step;     /* param.step: initial FISTA step                   */
+    double tol;      /* param.tol: relative objective change that stops  */
+    int backtrack;   /* param.backtrack                                  */
+    double tv_tol;   /* 0 = toolbox default 10e-4                        */
+    int tv_maxit;    /* 0 = toolbox default 200                          */
+} qmri_lrtv_params;
+int qmri_lrtv(qmri_op* op, const void* y, int y_dtype, const qmri_lrtv_params* params, void* x_out, int x_dtype, int* iters_done,
+              double* final_step);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@
 #include "aux_kernels.h"
 #include "common.cuh"
 #include "conv_kernels.h"
+#include "lrtv_kernels.h"
 #include "match_kernel.h"
 #include "op_tables.h"
 #include "unetres.h"
@@ -1461,5 +1462,147 @@ extern "C" int qmri_recon_metrics(qmri_ctx* ctx, int N, int M, int C, const void
     };
     if (!rc) rc = body();
     raw.release(); wk.release(); pa.release(); pb.release(); part.release(); res.release();
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// LRTV baseline: FISTA with a total-variation prox (main_files/algorithms/LRTV/FISTA_deep.m:31-103,
+// unlocbox/prox/prox_tv.m:100-193; called at main_recon_tsmis_FFT.m:272-282)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct LrtvWork {
+    qmri_op* op;
+    qmri_ctx* ctx;
+    size_t n;         // N M L
+    size_t n2;        // stacked image: 2N x (M L)
+    int R, Cc;
+    DevBuf dbl, flt, ybuf, fx, part, sums;
+    double *xr, *xi, *x2r, *x2i, *pr, *pi, *b, *r, *s, *po, *qo, *sol;
+    float *fr, *fi, *gr, *gi;
+    double h[4];
+    int sync_sums() {
+        QCUDA(cudaMemcpyAsync(h, sums.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        QCUDA(cudaStreamSynchronize(ctx->stream));
+        return QMRI_OK;
+    }
+    // fx = F.forward(planes)
+    int forward(const float* re, const float* im) {
+        K1Params p = {};
+        k1_fill_tables(op, p);
+        p.mode = K1_FORWARD;
+        p.in_re = re; p.in_im = im;
+        p.y_out = fx.as<float2>();
+        return k1_dispatch(op, p, 1);
+    }
+    int adjoint(const float2* y, float* re, float* im) {
+        K1Params p = {};
+        k1_fill_tables(op, p);
+        p.mode = K1_ADJOINT;
+        p.y = y;
+        p.out_re = re; p.out_im = im;
+        return k1_dispatch(op, p, 1);
+    }
+    // prox_tv on x2 (in place); tv_tol / tv_maxit = the toolbox defaults the reference leaves untouched
+    int prox_tv(double gamma, double tol, int maxit) {
+        if (gamma == 0.0) return QMRI_OK;
+        const int N = op->N;
+        QCHECK(lrtv_stack(ctx, x2r, x2i, N, Cc, b));
+        QCUDA(cudaMemsetAsync(r, 0, n2 * sizeof(double) * 4, ctx->stream));  // r, s, pold, qold are contiguous
+        double told = 1.0, prev_obj = 0.0;
+        for (int it = 1; it <= maxit; ++it) {
+            const double t = (1.0 + sqrt(4.0 * told * told)) / 2.0;
+            QCHECK(lrtv_tv_sol(ctx, b, r, s, gamma, R, Cc, sol, part.as<double>(), sums.as<double>()));
+            QCHECK(lrtv_tv_update(ctx, sol, r, s, po, qo, gamma, (told - 1.0) / t, R, Cc, part.as<double>(), sums.as<double>()));
+            QCHECK(sync_sums());
+            const double obj = 0.5 * h[0] + gamma * h[1];
+            const double rel = fabs(obj - prev_obj) / obj;
+            prev_obj = obj;
+            if (rel < tol) break;   // the dual update launched above is simply not used
+            told = t;
+        }
+        return lrtv_unstack(ctx, sol, N, Cc, x2r, x2i);
+    }
+};
+}  // namespace
+
+extern "C" int qmri_lrtv(qmri_op* op, const void* y, int y_dtype, const qmri_lrtv_params* prm, void* x_out, int x_dtype, int* iters_done,
+                         double* final_step) {
+    if (!op || !y || !prm || !x_out) return qmri_fail(QMRI_EINVAL, "qmri_lrtv: null argument");
+    if (!dtype_is_complex(y_dtype) || !dtype_is_complex(x_dtype)) return qmri_fail(QMRI_EINVAL, "qmri_lrtv: y and x must be complex");
+    if (prm->iters < 0 || !(prm->step > 0.0) || prm->K < 0.0) return qmri_fail(QMRI_EINVAL, "qmri_lrtv: need iter >= 0, step > 0, K >= 0");
+    qmri_ctx* ctx = op->ctx;
+    DevSetter ds(ctx->device);
+    LrtvWork w;
+    w.op = op; w.ctx = ctx;
+    w.n = op->plane();
+    w.R = 2 * op->N;
+    w.Cc = op->M * op->C;
+    w.n2 = (size_t)w.R * w.Cc;
+    const size_t nm = std::max<size_t>((size_t)op->t.nmeas, 1);
+    int rc = w.dbl.ensure((6 * w.n + 6 * w.n2) * sizeof(double));
+    if (!rc) rc = w.flt.ensure(4 * w.n * sizeof(float));
+    if (!rc) rc = w.fx.ensure(nm * sizeof(float2));
+    if (!rc) rc = w.part.ensure(lrtv_partial_elems(w.n2) * sizeof(double));
+    if (!rc) rc = w.sums.ensure(4 * sizeof(double));
+    auto body = [&]() -> int {
+        double* d = w.dbl.as<double>();
+        w.xr = d; w.xi = d + w.n; w.x2r = d + 2 * w.n; w.x2i = d + 3 * w.n; w.pr = d + 4 * w.n; w.pi = d + 5 * w.n;
+        d += 6 * w.n;
+        w.b = d; w.r = d + w.n2; w.s = d + 2 * w.n2; w.po = d + 3 * w.n2; w.qo = d + 4 * w.n2; w.sol = d + 5 * w.n2;
+        float* f = w.flt.as<float>();
+        w.fr = f; w.fi = f + w.n; w.gr = f + 2 * w.n; w.gi = f + 3 * w.n;
+        QCHECK(y_upload(op, y, y_dtype, 1));
+        const float2* yd = op->ybuf.as<float2>();
+        QCUDA(cudaMemsetAsync(w.dbl.p, 0, 6 * w.n * sizeof(double), ctx->stream));   // x = 0, x2_prev = 0
+        QCUDA(cudaMemsetAsync(w.flt.p, 0, 2 * w.n * sizeof(float), ctx->stream));
+        QCUDA(cudaMemsetAsync(w.sums.p, 0, 4 * sizeof(double), ctx->stream));
+        double step = prm->step, obj_prev = 0.0;
+        const double tv_tol = prm->tv_tol > 0.0 ? prm->tv_tol : 10e-4;
+        const int tv_maxit = prm->tv_maxit > 0 ? prm->tv_maxit : 200;
+        int it = 0;
+        for (it = 1; it <= prm->iters; ++it) {
+            // err = F.forward(x) - y; grad1 = F.adjoint(err); cvxobj = |err|^2 / 2; val = |x|_TV          (FISTA_deep.m:55-62)
+            QCHECK(w.forward(w.fr, w.fi));
+            QCHECK(lrtv_residual(ctx, w.fx.as<float2>(), yd, (size_t)op->t.nmeas, w.part.as<double>(), w.sums.as<double>(), 2));
+            QCHECK(w.adjoint(w.fx.as<float2>(), w.gr, w.gi));
+            QCHECK(lrtv_stack(ctx, w.xr, w.xi, op->N, w.Cc, w.b));
+            QCHECK(lrtv_norm_tv(ctx, w.b, w.R, w.Cc, w.part.as<double>(), w.sums.as<double>(), 3));
+            QCHECK(w.sync_sums());
+            const double cvxobj = 0.5 * w.h[2], val = w.h[3];
+            for (;;) {                                                                                   // :66-88
+                QCHECK(lrtv_grad_step(ctx, w.xr, w.xi, w.gr, w.gi, step, w.n, w.x2r, w.x2i));
+                if (prm->K > 0.0) QCHECK(w.prox_tv(step * prm->K, tv_tol, tv_maxit));
+                if (!prm->backtrack) break;
+                // tmp = |F.forward(x2) - y|^2 / 2
+                DevBuf& tmpf = op->a_re;  // scratch planes of the operator's host entry points
+                QCHECK(tmpf.ensure(2 * w.n * sizeof(float)));
+                float* tr = tmpf.as<float>();
+                float* ti = tr + w.n;
+                QCHECK(lrtv_to_float(ctx, w.x2r, w.x2i, w.n, tr, ti));
+                QCHECK(w.forward(tr, ti));
+                QCHECK(lrtv_residual(ctx, w.fx.as<float2>(), yd, (size_t)op->t.nmeas, w.part.as<double>(), w.sums.as<double>(), 2));
+                QCHECK(lrtv_backtrack_terms(ctx, w.xr, w.xi, w.x2r, w.x2i, w.gr, w.gi, w.n, w.part.as<double>(), w.sums.as<double>()));
+                QCHECK(w.sync_sums());
+                const double tmp = 0.5 * w.h[2];
+                if (tmp > cvxobj + w.h[0] + w.h[1] / (2.0 * step)) step *= 0.5;  // 'reducing stepsize...'
+                else break;
+            }
+            // x = x2 + (t-1)/(t+2) (x2 - x2_prev)                                                       (:90-93)
+            QCHECK(lrtv_momentum(ctx, w.xr, w.xi, w.x2r, w.x2i, w.pr, w.pi, (double)(it - 1) / (double)(it + 2), w.n, w.fr, w.fi));
+            const double obj = cvxobj + prm->K * val;
+            if (fabs(obj - obj_prev) / obj < prm->tol) break;                                            // :98
+            obj_prev = obj;
+        }
+        if (iters_done) *iters_done = std::min(it, prm->iters);
+        if (final_step) *final_step = step;
+        // the loop's x (after the momentum step, :90) is what FISTA_deep returns
+        QCHECK(op->stage.ensure(w.n * dtype_size(x_dtype)));
+        QCHECK(aux_pack_f64(ctx, op->stage.p, x_dtype, w.xr, w.xi, w.n));
+        QCUDA(cudaMemcpyAsync(x_out, op->stage.p, w.n * dtype_size(x_dtype), cudaMemcpyDeviceToHost, ctx->stream));
+        QCUDA(cudaStreamSynchronize(ctx->stream));
+        return QMRI_OK;
+    };
+    if (!rc) rc = body();
+    w.dbl.release(); w.flt.release(); w.fx.release(); w.part.release(); w.sums.release();
     return rc;
 }

@@ -32,6 +32,11 @@ DENOISE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C
                          C.c_int, C.c_void_p)
 
 
+class LrtvParams(C.Structure):
+    _fields_ = [("K", C.c_double), ("iters", C.c_int), ("step", C.c_double), ("tol", C.c_double), ("backtrack", C.c_int),
+                ("tv_tol", C.c_double), ("tv_maxit", C.c_int)]
+
+
 class AdmmParams(C.Structure):
     _fields_ = [("iters", C.c_int), ("gamma", C.c_double), ("cg_tol", C.c_double), ("multi_level", C.c_int),
                 ("noise_map", C.c_void_p), ("net", C.c_void_p), ("fn", DENOISE_FN), ("user", C.c_void_p),
@@ -86,6 +91,7 @@ SIGNATURES = {
     "qmri_awgn": (_i, [_vp, _vp, _i, _i64, _i, _d, C.c_uint64]),
     "qmri_awgn_dev": (_i, [_vp, _vp, _i64, _i, _d, C.c_uint64, _vp]),
     "qmri_foreground_mask": (_i, [_vp, _vp, _i, _i, _i, _d, _vp]),
+    "qmri_lrtv": (_i, [_vp, _vp, _i, C.POINTER(LrtvParams), _vp, _i, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "qmri_recon_metrics": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
 }
 

@@ -267,3 +267,33 @@ def test_shard_resident_dictionary_equals_whole(q):
     for s in shards:
         s.close()
     whole.close()
+
+
+# ---- LRTV baseline (FISTA_deep.m + prox_tv; main_recon_tsmis_FFT.m:272-282) ------------------------------------------------------
+@pytest.mark.parametrize("kind", ["spiral", "epi"])
+def test_lrtv_matches_oracle(q, kind):
+    import bench
+    from oracle import lrtv, sampling
+    V = np.eye(10)
+    if kind == "spiral":
+        P, Po = q.setup_subsampling_spiralgrided(224, 224, 771, V), sampling.setup_subsampling_spiralgrided(224, 224, 771, V)
+    else:
+        P, Po = q.setup_subsampling_epi(224, 224, 1 / 65, V), sampling.setup_subsampling_epi(224, 224, 1 / 65, V)
+    F, Fo = q.fft_operator(P), sampling.FOperator(Po)
+    X0 = bench.synthetic_slices(1, 11)[..., 0]
+    Y = q.awgn(Fo.forward(X0), 30.0, "measured", seed=3)
+    step0 = X0.size / Y.size                                             # param.step = numel(X0)/numel(Y)
+    param = {"K": 4e-5, "iter": 5, "step": step0, "tol": 1e-4, "backtrack": 1}
+    data = {"N": 224, "M": 224, "L": 10, "y": Y, "F": F, "D": []}
+    x, info = q.FISTA_deep(data, param, return_info=True)
+    trace = []
+    xo, its = lrtv.fista_lrtv(Y, Fo, X0.shape, K=4e-5, max_iter=5, step=step0, tol=1e-4, backtrack=True, trace=trace)
+    assert info["iter"] == its and info["step"] == trace[-1]["step"]      # same backtracking decisions (step halved 7 times from 81)
+    assert x.shape == (224, 224, 10) and x.dtype == np.complex128
+    assert rel_l2(x, xo) < 1e-4                                           # operator in fp32, TV prox in double on both sides
+    # K = 0: plain FISTA on the data term, no prox
+    x0, _ = q.FISTA_deep(data, dict(param, K=0.0, iter=3), return_info=True)
+    xo0, _ = lrtv.fista_lrtv(Y, Fo, X0.shape, K=0.0, max_iter=3, step=step0, tol=1e-4, backtrack=True)
+    assert rel_l2(x0, xo0) < 1e-5
+    with pytest.raises(KeyError):
+        q.FISTA_deep(data, {"K": 1e-5, "iter": 2})
