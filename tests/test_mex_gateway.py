@@ -108,7 +108,9 @@ def test_mex_gateway_matches_ctypes_path(split):
     assert xm.shape == (224, 224, 10) and np.array_equal(xm, xq)
     from oracle import unetres
     sd = unetres.make_state_dict(10, seed=0)
-    hn = m.call("net_load", 10, [sd[k].numpy() for k, _ in q.state_dict_keys(10)])
+    # a MATLAB caller hands every weight tensor over in PyTorch MEMORY order: the array [kw kh Cin Cout] (column-major) of the
+    # tensor [Cout Cin kh kw] (row-major) - here the transposed view, which is Fortran-contiguous over the same bytes
+    hn = m.call("net_load", 10, [sd[k].numpy().T for k, _ in q.state_dict_keys(10)])
     m.call("net_precision", hn, 1, nlhs=0)
     net = q.UNetRes(sd, in_nc=10)
     net.set_precision("tc")
