@@ -185,6 +185,10 @@ int qmri_admm_state_dev(qmri_admm* st, const float** x_re, const float** x_im);
 int qmri_admm_destroy(qmri_admm* st);
 /* Kernel-only x-update step on a resident state (w, v) -> w' ; used by bench.py for the K1 roofline. */
 int qmri_admm_xupdate_only(qmri_admm* st, int reps);
+/* Algorithmic HBM bytes per pixel-channel of one x-update in the state formulation this session runs: 8 for the real-state
+ * loop (read v, write Re w'; two slices or more, V = eye: csrc/xupdate_real.cu), 20 for the complex-state kernels (read w and v,
+ * write w').  bench.py reports the x-update roofline against this figure, never against bytes that do not move. */
+int qmri_admm_xupdate_bytes(qmri_admm* st);
 
 /* ---- dictionary matching ---------------------------------------------------------
  * Replaces out = mrf_dtm_cpu(dict, data, par)   main_files/dictionary_matching/mrf_dtm_cpu.m:1-166

@@ -20,4 +20,7 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(stream); sess.xupdate_only(reps); e1.record(stream); torch.cuda.synchronize()
 t = e0.elapsed_time(e1) / reps * 1e-3
-print(f"K1 S={S}: {t*1e6/S:.3f} us per slice-iteration, {20.0*224*224*10*S/t/1e9:.1f} GB/s algorithmic (20 B/px-ch)")
+bpp = float(sess.xupdate_bytes())   # algorithmic bytes per pixel-channel of the formulation that ran (8: real state, 20: complex state)
+state = "real" if bpp == 8 else "complex"
+print(f"K1 S={S} state={state} group={os.environ.get('QMRI_K1R_GROUP', 'default')} G={os.environ.get('QMRI_K1R_G', 'auto')}: "
+      f"{t*1e6/S:.3f} us per slice-iteration, {bpp*224*224*10*S/t/1e9:.1f} GB/s algorithmic ({bpp:.0f} B/px-ch)")

@@ -21,11 +21,24 @@ npix = 224 * 224
 reps = int(os.environ.get("K2_REPS", "5"))
 for K in Ks:
     rng = np.random.default_rng(0)
-    D = rng.standard_normal((K, 10)).astype(np.float32)
-    D /= np.linalg.norm(D, axis=1, keepdims=True)
-    d = q.Dictionary({"D": D, "normD": np.ones(K, np.float32), "lut": rng.random((K, 2)).astype(np.float32)}, ctx=ctx)
-    xr = torch.randn(10 * npix, device="cuda")
-    xi = torch.randn(10 * npix, device="cuda")
+    kind = os.environ.get("K2_DICT", "random")
+    if kind == "mrf":   # the synthetic FISP-like dictionary of the benchmark: atoms ordered along (T1, T2), scores vary smoothly with the index
+        import benchdata
+        dd = benchdata.make_dictionary(K_target=K, cut=3, seed=0)
+        D = dd["D"]
+        K = D.shape[0]
+        d = q.Dictionary(dd, ctx=ctx)
+        idx = rng.integers(0, K, npix)
+        X = D[idx].astype(np.float64) * rng.uniform(0.3, 1.0, (npix, 1)) * np.exp(1j * rng.uniform(0, 2 * np.pi, (npix, 1)))
+        X = X + 0.02 * np.abs(X).max() * (rng.standard_normal(X.shape) + 1j * rng.standard_normal(X.shape))
+        xr = torch.from_numpy(np.ascontiguousarray(X.real.T.astype(np.float32))).cuda().reshape(-1)
+        xi = torch.from_numpy(np.ascontiguousarray(X.imag.T.astype(np.float32))).cuda().reshape(-1)
+    else:
+        D = rng.standard_normal((K, 10)).astype(np.float32)
+        D /= np.linalg.norm(D, axis=1, keepdims=True)
+        d = q.Dictionary({"D": D, "normD": np.ones(K, np.float32), "lut": rng.random((K, 2)).astype(np.float32)}, ctx=ctx)
+        xr = torch.randn(10 * npix, device="cuda")
+        xi = torch.randn(10 * npix, device="cuda")
     keys = {}
     for pipe in os.environ.get("K2_PIPES", "fma,tensor").split(","):
         os.environ["QMRI_K2_PIPE"] = pipe
@@ -44,7 +57,7 @@ for K in Ks:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         keys[pipe] = k.clone()
-        print(f"K = {K:8d} pipe {pipe:6s}: {ms:8.3f} ms per slice, {npix * K / (ms * 1e-3):.3e} px-atoms/s, {npix * K / (ms * 1e-3) / (148 * 1.965e9):.2f} scores/clk/SM")
+        print(f"K = {K:8d} ({kind}) pipe {pipe:6s}: {ms:8.3f} ms per slice, {npix * K / (ms * 1e-3):.3e} px-atoms/s, {npix * K / (ms * 1e-3) / (148 * 1.965e9):.2f} scores/clk/SM")
     if len(keys) == 2:
         a, b = keys["fma"], keys["tensor"]
         print(f"           identical keys on {float((a == b).float().mean()):.5f} of the pixels")

@@ -272,6 +272,114 @@ static void emulate_stream(int mode, int C, int S, const optab::K1Tables& t, con
     }
 }
 
+// Real-image streaming kernels (xupdate_real.cu), thread by thread: op 0 = forward (y_out = A v), op 1 = adjoint
+// (out = v + Re(A^H c), c handed over in `y`).  Same phase functions, folded-row tables and scalings as the CUDA kernels.
+static void emulate_real(int op, int C, int S, const optab::K1Tables& t, const float* v, const float* y, float* out, float* y_out,
+                         float* minmax) {
+    constexpr int PC = 14, THREADS = 16 * PC, SLABS = NF / (2 * PC), G = 2, SPC = SLABS / G;
+    const float2* tw2 = reinterpret_cast<const float2*>(t.tw2.data());
+    const float2* tw448 = reinterpret_cast<const float2*>(t.tw448.data());
+    const size_t plane = (size_t)NF * NF;
+    const float inv_n = 1.0f / (float)NF;
+    for (int s = 0; s < S; ++s) {
+        float lmin = INFINITY, lmax = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+            const int f0 = t.frame_ptr[c], ns = t.frame_ptr[c + 1] - f0;
+            const size_t img = ((size_t)(s * C + c)) * plane;
+            const uint32_t* ent = t.r_ent.data() + f0;
+            const uint32_t* itA = t.r_itA.data() + (size_t)c * NF;
+            const uint32_t* itB = t.r_itB.data() + (size_t)c * NF;
+            std::vector<float2> regs((size_t)THREADS * 16);
+            auto A = [&](int tid) -> float2(&)[16] { return *reinterpret_cast<float2(*)[16]>(&regs[(size_t)tid * 16]); };
+            if (op == 0) {
+                std::vector<std::vector<float2>> part(G, std::vector<float2>((size_t)t.ns_max + 1, float2{0, 0}));
+                for (int g = 0; g < G; ++g) {
+                    std::vector<float2> ws((size_t)PC * CS, float2{0, 0});
+                    for (int sl = 0; sl < SPC; ++sl) {
+                        const int m0 = (g * SPC + sl) * 2 * PC;
+                        for (int tid = 0; tid < THREADS; ++tid) {
+                            const int l16 = tid & 15, col = tid >> 4;
+                            const size_t gi = img + (size_t)(m0 + 2 * col) * NF + l16;
+                            float2(&a)[16] = A(tid);
+                            for (int n1 = 0; n1 < 14; ++n1) a[n1] = float2{v[gi + 16 * n1], v[gi + NF + 16 * n1]};
+                            fwd_s1_regs(a, l16, tw2);
+                        }
+                        for (int tid = 0; tid < THREADS; ++tid) fft_s1_store(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
+                        for (int tid = 0; tid < THREADS; ++tid)
+                            if ((tid & 15) < 14) fft_s2_load(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
+                        for (int tid = 0; tid < THREADS; ++tid)
+                            if ((tid & 15) < 14) fft_s2_store<false>(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
+                        for (int tid = 0; tid < THREADS; ++tid)
+                            p3r_item(ws.data(), (int)(itA[tid] & 0xffu), ent + (itA[tid] >> 16), (int)((itA[tid] >> 8) & 0xffu), tw448, m0, part[g].data());
+                    }
+                }
+                for (int j = 0; j < ns; ++j) {
+                    const size_t yi = (size_t)s * t.nmeas + f0 + j;
+                    float sx = 0.f, sy = 0.f;
+                    for (int g = 0; g < G; ++g) {
+                        sx += part[g][j].x;
+                        sy += part[g][j].y;
+                    }
+                    y_out[2 * yi] = sx * (0.5f * inv_n);
+                    y_out[2 * yi + 1] = sy * (0.5f * inv_n);
+                }
+                continue;
+            }
+            std::vector<float2> cvec((size_t)t.ns_max + 1, float2{0, 0});
+            for (int j = 0; j < ns; ++j) {
+                const size_t yi = (size_t)s * t.nmeas + f0 + j;
+                cvec[j] = float2{y[2 * yi] * (0.5f * inv_n), y[2 * yi + 1] * (0.5f * inv_n)};
+            }
+            for (int g = 0; g < G; ++g) {
+                std::vector<float2> ws((size_t)PC * CS, float2{0, 0});
+                std::vector<float2> ovf((size_t)std::max(t.r_n_ovf, 1) * 2 * OVF_STRIDE, float2{0, 0});
+                for (int sl = 0; sl < SPC; ++sl) {
+                    const int m0 = (g * SPC + sl) * 2 * PC;
+                    for (auto& e : ws) e = float2{NAN, NAN};  // rows outside the symmetric row mask are never written nor read
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        const int k1row = (int)(itA[tid] & 0xffu), cnt = (int)((itA[tid] >> 8) & 0xffu), slot = (int)(itB[tid] & 0xffu);
+                        if (k1row == 255) continue;
+                        for (int h = 0; h < 2; ++h) {
+                            float2 SP[NP_STREAM], SM[NP_STREAM];
+                            p4r_item_partial(SP, SM, ent + (itA[tid] >> 16), cnt, tw448, m0 + 14 * h, cvec.data());
+                            if (slot == 0) p4r_store<false>(ws.data(), k1row, h, SP, SM);
+                            else p4_item_spill(ovf.data() + ((size_t)(slot - 1) * 2 + h) * OVF_STRIDE, SP, SM);
+                        }
+                    }
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        const int k1row = (int)(itA[tid] & 0xffu), slot = (int)(itB[tid] & 0xffu);
+                        const int novf = (int)((itB[tid] >> 8) & 0xffu), ovf0 = (int)((itB[tid] >> 16) & 0xffu);
+                        if (k1row != 255 && slot == 0 && novf)
+                            for (int h = 0; h < 2; ++h)
+                                p4r_row_add_overflow(ws.data(), k1row, h, ovf.data() + ((size_t)ovf0 * 2 + h) * OVF_STRIDE, novf, 2 * OVF_STRIDE);
+                    }
+                    for (int tid = 0; tid < THREADS; ++tid)
+                        if ((tid & 15) < 14) inv_s1_load(ws.data() + (tid >> 4) * CS, tid & 15, tw2, t.r_rowmask[(size_t)c * 16 + (tid & 15)], A(tid));
+                    for (int tid = 0; tid < THREADS; ++tid)
+                        if ((tid & 15) < 14) inv_s1_store(ws.data() + (tid >> 4) * CS, tid & 15, A(tid));
+                    for (int tid = 0; tid < THREADS; ++tid) {
+                        const int l16 = tid & 15, col = tid >> 4;
+                        const size_t gi = img + (size_t)(m0 + 2 * col) * NF + l16;
+                        float2(&a)[16] = A(tid);
+                        inv_s2_regs(ws.data() + col * CS, l16, a);
+                        for (int d = 0; d < 14; ++d) {
+                            const float oa = v[gi + 16 * d] + a[d].x, ob = v[gi + NF + 16 * d] + a[d].y;
+                            out[gi + 16 * d] = oa;
+                            out[gi + NF + 16 * d] = ob;
+                            lmin = fminf(lmin, fminf(oa, ob));
+                            lmax = fmaxf(lmax, fmaxf(oa, ob));
+                        }
+                    }
+                }
+            }
+        }
+        if (minmax) {
+            minmax[2 * s] = lmin;
+            minmax[2 * s + 1] = lmax;
+        }
+    }
+}
+
 extern "C" {
 
 // pattern: 0 = spiral(S_curve = (int)arg), 1 = epi(percentage = arg).  Returns nmeas; fills idx/frame_ptr when non-null.
@@ -307,6 +415,22 @@ int k1emu_run(int mode, int mc, int pattern, double arg, int C, int S, const flo
     }
     if (mc == 56) emulate<56>(mode, C, S, t, in_re, in_im, v, y, rho, out_re, out_im, y_out, minmax);
     else emulate<28>(mode, C, S, t, in_re, in_im, v, y, rho, out_re, out_im, y_out, minmax);
+    return t.nmeas;
+}
+
+// real-image kernels: op 0 forward (v -> y_out), op 1 adjoint (c in y, out = v + Re(A^H c)).  Returns nmeas, -1 if the mask does
+// not fit the folded work-item tables; *n_ovf receives the overflow-slot count (what sizes the kernels' shared memory).
+int k1emu_run_real(int op, int pattern, double arg, int C, int S, const float* v, const float* y, float* out, float* y_out, float* minmax,
+                   int* n_ovf) {
+    std::vector<std::vector<int32_t>> frames;
+    if (pattern == 0) optab::spiral_frames(NF, (int)arg, C, frames);
+    else optab::epi_frames(NF, NF, arg, C, frames);
+    optab::K1Tables t;
+    const char* env = getenv("QMRI_K1_QMIN");
+    optab::build_k1_tables(NF, frames, t, env ? atoi(env) : 8);
+    if (!t.real_ok) return -1;
+    if (n_ovf) *n_ovf = t.r_n_ovf;
+    emulate_real(op, C, S, t, v, y, out, y_out, minmax);
     return t.nmeas;
 }
 

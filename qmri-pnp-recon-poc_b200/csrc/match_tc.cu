@@ -14,11 +14,12 @@
 // Kernel: persistent, warp-specialised.  Work item = (tile of 128 pixels, atom range).  Warp 0 (TMA): the pixel tile (real and
 // imaginary K-major rows, 2 x 16 KB, loaded once per work item) and a ring of 128-atom tiles (16 KB each) into 128B-swizzled
 // shared memory.  Warp 1 (MMA): per atom tile 2 x 4 tcgen05.mma (M128 x N128 x K8) into one of two TMEM accumulator pairs.
-// Warps 2-5 (epilogue): thread = pixel; tcgen05.ld of the real and imaginary accumulators, s = re^2 + im^2, running maximum of
-// 16-atom groups (3 FP32 instructions per score); a group that beats the thread's current fourth-best score is rescanned and
-// inserted into a sorted top-4 (strict comparisons: earlier atoms stay ahead on exact ties).  At the end of the work item the
-// four candidates are rescored with k2_score() - the FP32 FMA kernel's exact expression on the ORIGINAL fp32 atoms and pixels -
-// and the best becomes the packed key  float_bits(score) << 32 | (0xFFFFFFFF - atom), merged with atomicMax like the FMA
+// Warps 2-5 (epilogue): thread = pixel; tcgen05.ld of the real and imaginary accumulators (issued one 32-column chunk ahead of
+// the arithmetic), s = re^2 + im^2, running maximum of 16-atom groups (3 FP32 instructions per score); the thread keeps the TWO
+// BEST GROUPS by group maximum (strict comparisons: earlier groups stay ahead on exact ties; a per-atom top-k list degenerates on
+// real dictionaries, whose scores rise smoothly along the atom index so that nearly every group enters the list).  At the
+// end of the work item the 32 candidate atoms are rescored with k2_score() - the FP32 FMA kernel's exact expression on the
+// ORIGINAL fp32 atoms and pixels - and the best becomes the packed key  float_bits(score) << 32 | (0xFFFFFFFF - atom), merged with atomicMax like the FMA
 // kernel's (same keys, so atom ranges, kernels and ranks mix freely).
 #include <cuda.h>
 #include <math.h>
@@ -59,30 +60,6 @@ struct MtParams {
     int CP;
     unsigned long long* keys;
 };
-
-struct Top4 {
-    float s[4];
-    int k[4];
-};
-__device__ __forceinline__ void top4_insert(Top4& t, float s, int k) {
-    if (!(s > t.s[3])) return;  // also drops NaN
-    if (s > t.s[2]) {
-        t.s[3] = t.s[2]; t.k[3] = t.k[2];
-        if (s > t.s[1]) {
-            t.s[2] = t.s[1]; t.k[2] = t.k[1];
-            if (s > t.s[0]) {
-                t.s[1] = t.s[0]; t.k[1] = t.k[0];
-                t.s[0] = s; t.k[0] = k;
-            } else {
-                t.s[1] = s; t.k[1] = k;
-            }
-        } else {
-            t.s[2] = s; t.k[2] = k;
-        }
-    } else {
-        t.s[3] = s; t.k[3] = k;
-    }
-}
 
 // x planar [C][npix] -> K-major operand rows [part][npix_pad][32] = [hi | lo | hi | 0 0] (part 0 = real, 1 = imaginary)
 __global__ void match_prep_kernel(const float* __restrict__ x_re, const float* __restrict__ x_im, int64_t npix, int64_t npix_pad, int C,
@@ -225,54 +202,80 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int pt = w / p.nsplit, split = w - pt * p.nsplit;
             const int t0 = (int)(((int64_t)split * p.ntiles) / p.nsplit), t1 = (int)(((int64_t)(split + 1) * p.ntiles) / p.nsplit);
-            Top4 top;
+            // the two best 16-atom groups by their largest score (strict comparisons: the earlier group stays ahead on exact ties)
+            float g1s = -1.f, g2s = -1.f;
+            int g1k = -1, g2k = -1;
+            auto score_chunk = [&](const uint32_t (&re)[32], const uint32_t (&im)[32], int gid) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                top.s[i] = -1.f;
-                top.k[i] = -1;
-            }
-            for (int t = t0; t < t1; ++t, ++it) {
-                const int ab = it & 1;
-                mbar_wait(&tfull[ab], (it >> 1) & 1);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * 2 * MT_BN);
-#pragma unroll 1
-                for (int c0 = 0; c0 < MT_BN; c0 += 32) {
-                    uint32_t re[32], im[32];
-                    tc_ld32(taddr + c0, re);
-                    if (CPLX) tc_ld32(taddr + MT_BN + c0, im);
-                    tc_wait_ld();
-                    if (c0 == MT_BN - 32) {  // every accumulator value of this tile is in registers: hand the buffer back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[ab]);
-                    }
+                for (int g = 0; g < 2; ++g) {
+                    float gmax = -1.f;
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        float sc[16];
-                        float gmax = -1.f;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float a = __uint_as_float(re[16 * g + j]);
-                            if (CPLX) {
-                                const float b = __uint_as_float(im[16 * g + j]);
-                                sc[j] = fmaf(b, b, a * a);
-                            } else {
-                                sc[j] = a * a;
-                            }
-                            gmax = fmaxf(gmax, sc[j]);  // fmaxf drops NaN
+                    for (int j = 0; j < 16; ++j) {
+                        const float a = __uint_as_float(re[16 * g + j]);
+                        float sc;
+                        if (CPLX) {
+                            const float b = __uint_as_float(im[16 * g + j]);
+                            sc = fmaf(b, b, a * a);
+                        } else {
+                            sc = a * a;
                         }
-                        if (gmax > top.s[3]) {
-                            const int kb = t * MT_BN + c0 + 16 * g;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) top4_insert(top, sc[j], kb + j);
+                        gmax = fmaxf(gmax, sc);  // fmaxf drops NaN
+                    }
+                    if (gmax > g2s) {
+                        if (gmax > g1s) {
+                            g2s = g1s;
+                            g2k = g1k;
+                            g1s = gmax;
+                            g1k = gid + g;
+                        } else {
+                            g2s = gmax;
+                            g2k = gid + g;
                         }
                     }
                 }
+            };
+            auto load_chunk = [&](uint32_t taddr, uint32_t (&re)[32], uint32_t (&im)[32]) {
+                tc_ld32(taddr, re);
+                if (CPLX) tc_ld32(taddr + MT_BN, im);
+            };
+            // Accumulator reads run one 32-column chunk ahead of the arithmetic: a chunk's tcgen05.ld is issued before the previous
+            // chunk is scored and waited for afterwards (tcgen05.wait::ld covers every outstanding load of the thread).
+            uint32_t reA[32], imA[32], reB[32], imB[32];
+            auto tile_addr = [&](int i) { return tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((i & 1) * 2 * MT_BN); };
+            if (t0 < t1) {
+                mbar_wait(&tfull[it & 1], (it >> 1) & 1);
+                tc_fence_after();
+                load_chunk(tile_addr(it), reA, imA);
+                tc_wait_ld();
             }
-            // rescore the candidates with the FMA kernel's exact expression on the original fp32 data
+            for (int t = t0; t < t1; ++t, ++it) {
+                const int ab = it & 1;
+                const uint32_t taddr = tile_addr(it);
+                const int gid = (t - t0) * (MT_BN / 16);
+                load_chunk(taddr + 32, reB, imB);
+                score_chunk(reA, imA, gid);
+                tc_wait_ld();
+                load_chunk(taddr + 64, reA, imA);
+                score_chunk(reB, imB, gid + 2);
+                tc_wait_ld();
+                load_chunk(taddr + 96, reB, imB);
+                score_chunk(reA, imA, gid + 4);
+                tc_wait_ld();
+                // every accumulator value of this tile is in registers: hand the buffer back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[ab]);
+                if (t + 1 < t1) {
+                    mbar_wait(&tfull[(it + 1) & 1], ((it + 1) >> 1) & 1);
+                    tc_fence_after();
+                    load_chunk(tile_addr(it + 1), reA, imA);
+                }
+                score_chunk(reB, imB, gid + 6);
+                if (t + 1 < t1) tc_wait_ld();
+            }
+            // rescore the 2 x 16 candidates with the FMA kernel's exact expression on the original fp32 data
             const int64_t pix = (int64_t)pt * MT_BM + row;
-            if (pix < p.npix) {
+            if (pix < p.npix && g1k >= 0) {
                 float xr[C], xi[CPLX ? C : 1];
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -281,18 +284,23 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
                 }
                 float best = -1.f;
                 int64_t win = -1;
+#pragma unroll 1
+                for (int i = 0; i < 2; ++i) {
+                    const int gk = i ? g2k : g1k;
+                    if (gk < 0) continue;
+                    const int64_t kbase = p.a0 + ((int64_t)t0 * MT_BN) + (int64_t)gk * 16;
+#pragma unroll 4
+                    for (int j = 0; j < 16; ++j) {
+                        const int64_t k = kbase + j;
+                        if (k >= p.a1) break;  // zero rows that pad the last atom tile
+                        float d[C];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (top.k[i] < 0) continue;
-                    const int64_t k = p.a0 + top.k[i];
-                    if (k >= p.a1) continue;  // zero rows that pad the last atom tile
-                    float d[C];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) d[c] = __ldg(p.Dp + k * p.CP + c);
-                    const float s = k2_score<C, CPLX>(d, xr, xi);
-                    if (s > best || (s == best && k < win)) {
-                        best = s;
-                        win = k;
+                        for (int c = 0; c < C; ++c) d[c] = __ldg(p.Dp + k * p.CP + c);
+                        const float s = k2_score<C, CPLX>(d, xr, xi);
+                        if (s > best || (s == best && k < win)) {
+                            best = s;
+                            win = k;
+                        }
                     }
                 }
                 if (win >= 0 && best >= 0.f) {

@@ -85,6 +85,13 @@ struct K1Tables {
     std::vector<uint16_t> rowmask;    // [C][16] bit a of entry b: row 14 a + b holds samples (inverse FFT stage 1 skips empty rows)
     int n_ovf = 0;                    // largest number of overflow partials in one frame
     int max_row = 0;                  // largest number of samples in one row of one frame
+    // real-image variant of the streaming kernels (xupdate_real.cu): the same work-item tables over FOLDED rows.  For a real image
+    // the n-direction transform is Hermitian, T(N - k1, m) = conj T(k1, m), so a sample (k1 > N/2, k2) is carried by row N - k1 as
+    // (N - k2) mod N with its value conjugated: entries j | k2' << 16 | conj << 31, rows 0 .. N/2 only.
+    bool real_ok = false;
+    std::vector<uint32_t> r_itA, r_itB, r_ent;
+    std::vector<uint16_t> r_rowmask;  // [C][16] like rowmask, symmetric: row k and row N - k are set together
+    int r_n_ovf = 0;
     std::vector<float> tw2;           // [16][16][2]  e^{-2 pi i (i j) / N}
     std::vector<float> tw448;         // [2N][2]      e^{-2 pi i t / (2N)}
 };
@@ -106,6 +113,69 @@ constexpr int STREAM_OVF_MAX = 96;   // == k1::OVF_MAX_STREAM
 // without samples are zero-filled by a thread that is handed the row as a side duty.  Lane placement: thread 16 h + l takes
 // an item of residue class l (k1 = l mod 16) whenever one is left, heaviest first, so the 16 lanes of a half-warp address 16
 // different bank pairs in the [column][k1] workspace and the items of a warp carry similar sample counts.
+// Core of the work-item construction for one frame: `rows[k]` holds the entry words of row k (any row numbering < N).
+// Returns false when the frame does not fit (more than N items or too many overflow partials).
+static inline bool stream_items_for_frame(int N, const std::vector<std::vector<uint32_t>>& rows, int q_min, int ent_base, uint32_t* itA,
+                                          uint32_t* itB, std::vector<uint32_t>& ent, int& n_ovf) {
+    struct Item { int k1, first, cnt, chunk, nchunks, ovf0; };
+    int Q = 0;
+    for (int q = std::max(1, q_min); q <= STREAM_QMAX && !Q; ++q) {
+        int items = 0, ovf = 0;
+        for (int k = 0; k < N; ++k) {
+            int n = ((int)rows[k].size() + q - 1) / q;
+            items += n;
+            ovf += std::max(0, n - 1);
+        }
+        if (items <= N && ovf <= STREAM_OVF_MAX && ovf <= 254) Q = q;
+    }
+    if (!Q) return false;
+    std::vector<Item> items;
+    int slots = 0;
+    for (int k = 0; k < N; ++k) {
+        const int sz = (int)rows[k].size();
+        if (!sz) continue;
+        const int n = (sz + Q - 1) / Q;
+        int first = 0;
+        for (int ch = 0; ch < n; ++ch) {
+            const int cnt = sz / n + (ch < sz % n ? 1 : 0);  // even split
+            items.push_back({k, first, cnt, ch, n, slots});
+            first += cnt;
+        }
+        slots += n - 1;
+    }
+    n_ovf = std::max(n_ovf, slots);
+    // lane placement
+    std::vector<std::vector<int>> bucket(16);
+    for (int i = 0; i < (int)items.size(); ++i) bucket[items[i].k1 % 16].push_back(i);
+    for (auto& b : bucket) std::stable_sort(b.begin(), b.end(), [&](int a, int b2) { return items[a].cnt > items[b2].cnt; });
+    std::vector<int> place(N, -1), left;
+    const int H = N / 16;
+    for (int l = 0; l < 16; ++l)
+        for (int h = 0; h < (int)bucket[l].size(); ++h) {
+            if (h < H) place[16 * h + l] = bucket[l][h];
+            else left.push_back(bucket[l][h]);
+        }
+    std::stable_sort(left.begin(), left.end(), [&](int a, int b2) { return items[a].cnt > items[b2].cnt; });
+    for (int tid = 0, q = 0; tid < N && q < (int)left.size(); ++tid)
+        if (place[tid] < 0) place[tid] = left[q++];
+    // (rows without samples are skipped by the inverse FFT through `rowmask`: no zero fill)
+    size_t pos = 0;
+    for (int tid = 0; tid < N; ++tid) {
+        uint32_t A = 255u, B = 0u;
+        if (place[tid] >= 0) {
+            const Item& it = items[place[tid]];
+            A = (uint32_t)it.k1 | ((uint32_t)it.cnt << 8) | ((uint32_t)pos << 16);
+            const int slot = it.chunk == 0 ? 0 : it.ovf0 + it.chunk;  // overflow slots are numbered from 1
+            const int novf = it.chunk == 0 ? it.nchunks - 1 : 0;
+            B |= (uint32_t)slot | ((uint32_t)novf << 8) | ((uint32_t)it.ovf0 << 16);
+            for (int q = 0; q < it.cnt; ++q) ent[ent_base + pos++] = rows[it.k1][it.first + q];
+        }
+        itA[tid] = A;
+        itB[tid] = B;
+    }
+    return true;
+}
+
 static inline void build_stream_tables(int N, const std::vector<std::vector<int32_t>>& frames, K1Tables& t, int q_min = 1) {
     t.stream_ok = (N % 16 == 0) && N <= 254;
     t.itA.assign((size_t)t.C * N, 255u);
@@ -114,74 +184,39 @@ static inline void build_stream_tables(int N, const std::vector<std::vector<int3
     t.rowmask.assign((size_t)t.C * 16, 0);
     t.n_ovf = 0;
     t.max_row = 0;
+    t.real_ok = t.stream_ok && N == 224;
+    t.r_itA.assign((size_t)t.C * N, 255u);
+    t.r_itB.assign((size_t)t.C * N, 0u);
+    t.r_ent.assign(std::max(t.nmeas, 1), 0);
+    t.r_rowmask.assign((size_t)t.C * 16, 0);
+    t.r_n_ovf = 0;
     if (!t.stream_ok) return;
-    struct Item { int k1, first, cnt, chunk, nchunks, ovf0; };
     for (int c = 0; c < t.C; ++c) {
         const auto& f = frames[c];
-        std::vector<std::vector<uint32_t>> rows(N);
-        for (int j = 0; j < (int)f.size(); ++j) rows[f[j] % N].push_back((uint32_t)j | ((uint32_t)(f[j] / N) << 16));
+        std::vector<std::vector<uint32_t>> rows(N), folded(N);
+        for (int j = 0; j < (int)f.size(); ++j) {
+            const int k1 = f[j] % N, k2 = f[j] / N;
+            rows[k1].push_back((uint32_t)j | ((uint32_t)k2 << 16));
+            if (2 * k1 <= N) folded[k1].push_back((uint32_t)j | ((uint32_t)k2 << 16));
+            else folded[N - k1].push_back((uint32_t)j | ((uint32_t)((N - k2) % N) << 16) | 0x80000000u);
+        }
         for (int k = 0; k < N; ++k) {
             t.max_row = std::max(t.max_row, (int)rows[k].size());
             if (!rows[k].empty() && N == 224) t.rowmask[(size_t)c * 16 + k % 14] |= (uint16_t)(1u << (k / 14));
-        }
-        int Q = 0;
-        for (int q = std::max(1, q_min); q <= STREAM_QMAX && !Q; ++q) {
-            int items = 0, ovf = 0;
-            for (int k = 0; k < N; ++k) {
-                int n = ((int)rows[k].size() + q - 1) / q;
-                items += n;
-                ovf += std::max(0, n - 1);
+            if (!folded[k].empty() && N == 224) {
+                const int kn = (N - k) % N;
+                t.r_rowmask[(size_t)c * 16 + k % 14] |= (uint16_t)(1u << (k / 14));
+                t.r_rowmask[(size_t)c * 16 + kn % 14] |= (uint16_t)(1u << (kn / 14));
             }
-            if (items <= N && ovf <= STREAM_OVF_MAX && ovf <= 254) Q = q;
         }
-        if (!Q) {
+        if (!stream_items_for_frame(N, rows, q_min, t.frame_ptr[c], t.itA.data() + (size_t)c * N, t.itB.data() + (size_t)c * N, t.ent, t.n_ovf)) {
             t.stream_ok = false;
+            t.real_ok = false;
             return;
         }
-        std::vector<Item> items;
-        int slots = 0;
-        for (int k = 0; k < N; ++k) {
-            const int sz = (int)rows[k].size();
-            if (!sz) continue;
-            const int n = (sz + Q - 1) / Q;
-            int first = 0;
-            for (int ch = 0; ch < n; ++ch) {
-                const int cnt = sz / n + (ch < sz % n ? 1 : 0);  // even split
-                items.push_back({k, first, cnt, ch, n, slots});
-                first += cnt;
-            }
-            slots += n - 1;
-        }
-        t.n_ovf = std::max(t.n_ovf, slots);
-        // lane placement
-        std::vector<std::vector<int>> bucket(16);
-        for (int i = 0; i < (int)items.size(); ++i) bucket[items[i].k1 % 16].push_back(i);
-        for (auto& b : bucket) std::stable_sort(b.begin(), b.end(), [&](int a, int b2) { return items[a].cnt > items[b2].cnt; });
-        std::vector<int> place(N, -1), left;
-        const int H = N / 16;
-        for (int l = 0; l < 16; ++l)
-            for (int h = 0; h < (int)bucket[l].size(); ++h) {
-                if (h < H) place[16 * h + l] = bucket[l][h];
-                else left.push_back(bucket[l][h]);
-            }
-        std::stable_sort(left.begin(), left.end(), [&](int a, int b2) { return items[a].cnt > items[b2].cnt; });
-        for (int tid = 0, q = 0; tid < N && q < (int)left.size(); ++tid)
-            if (place[tid] < 0) place[tid] = left[q++];
-        // (rows without samples are skipped by the inverse FFT through `rowmask`: no zero fill)
-        size_t pos = 0;
-        for (int tid = 0; tid < N; ++tid) {
-            uint32_t A = 255u, B = 0u;
-            if (place[tid] >= 0) {
-                const Item& it = items[place[tid]];
-                A = (uint32_t)it.k1 | ((uint32_t)it.cnt << 8) | ((uint32_t)pos << 16);
-                const int slot = it.chunk == 0 ? 0 : it.ovf0 + it.chunk;  // overflow slots are numbered from 1
-                const int novf = it.chunk == 0 ? it.nchunks - 1 : 0;
-                B |= (uint32_t)slot | ((uint32_t)novf << 8) | ((uint32_t)it.ovf0 << 16);
-                for (int q = 0; q < it.cnt; ++q) t.ent[t.frame_ptr[c] + pos++] = rows[it.k1][it.first + q];
-            }
-            t.itA[(size_t)c * N + tid] = A;
-            t.itB[(size_t)c * N + tid] = B;
-        }
+        if (t.real_ok && !stream_items_for_frame(N, folded, q_min, t.frame_ptr[c], t.r_itA.data() + (size_t)c * N, t.r_itB.data() + (size_t)c * N,
+                                                 t.r_ent, t.r_n_ovf))
+            t.real_ok = false;
     }
 }
 

@@ -277,6 +277,8 @@ struct qmri_op {
     uint32_t* d_itB = nullptr;
     uint32_t* d_ent = nullptr;
     uint16_t* d_rowmask = nullptr;
+    uint32_t *d_ritA = nullptr, *d_ritB = nullptr, *d_rent = nullptr;  // real-image streaming kernels (folded rows)
+    uint16_t* d_rrowmask = nullptr;
     int k1_kernel = 0;  // 0 = choose by batch size, 1 = cluster kernel, 2 = streaming kernel (QMRI_K1_KERNEL=cluster|stream)
     // general V (not the identity): channels are transformed on the union of the masks and mixed per k-space location
     bool general = false;
@@ -356,6 +358,10 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     r |= dev_alloc(&op->d_itB, t.itB.size());
     r |= dev_alloc(&op->d_ent, t.ent.size());
     r |= dev_alloc(&op->d_rowmask, t.rowmask.size());
+    r |= dev_alloc(&op->d_ritA, t.r_itA.size());
+    r |= dev_alloc(&op->d_ritB, t.r_itB.size());
+    r |= dev_alloc(&op->d_rent, t.r_ent.size());
+    r |= dev_alloc(&op->d_rrowmask, t.r_rowmask.size());
     if (op->general) {
         const optab::GeneralTables& g = op->g;
         const size_t nmf = std::max<size_t>(g.memb_frame.size(), 1);
@@ -390,6 +396,10 @@ static int op_from_frames(qmri_ctx* ctx, int N, int M, int C, int L, const std::
     cudaMemcpy(op->d_itB, t.itB.data(), sizeof(uint32_t) * t.itB.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_ent, t.ent.data(), sizeof(uint32_t) * t.ent.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(op->d_rowmask, t.rowmask.data(), sizeof(uint16_t) * t.rowmask.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_ritA, t.r_itA.data(), sizeof(uint32_t) * t.r_itA.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_ritB, t.r_itB.data(), sizeof(uint32_t) * t.r_itB.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_rent, t.r_ent.data(), sizeof(uint32_t) * t.r_ent.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_rrowmask, t.r_rowmask.data(), sizeof(uint16_t) * t.r_rowmask.size(), cudaMemcpyHostToDevice);
     cudaError_t e = cudaMemcpy(op->d_p4tab, t.p4tab.data(), sizeof(uint32_t) * t.p4tab.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         qmri_op_destroy(op);
@@ -432,6 +442,7 @@ extern "C" int qmri_op_destroy(qmri_op* op) {
     cudaFree(op->d_meas_frame); cudaFree(op->d_minv);
     for (auto& sd : op->gparts) sd.release();
     cudaFree(op->d_tw2); cudaFree(op->d_tw448); cudaFree(op->d_itA); cudaFree(op->d_itB); cudaFree(op->d_ent); cudaFree(op->d_rowmask);
+    cudaFree(op->d_ritA); cudaFree(op->d_ritB); cudaFree(op->d_rent); cudaFree(op->d_rrowmask);
     op->stage.release(); op->a_re.release(); op->a_im.release(); op->b_re.release(); op->b_im.release();
     op->c_re.release(); op->c_im.release(); op->ybuf.release(); op->mm_ord.release(); op->mm_f.release();
     op->k1_part.release(); op->k1_cbuf.release();
@@ -794,6 +805,11 @@ struct qmri_admm {
     qmri_admm_params prm;
     DevBuf y, x0_re, x0_im, w_re, w_im, v, x_re, x_im, mm_ord, mm_f, noise, cb_in, cb_out;
     DevBuf k1_part, k1_cbuf;  // streaming x-update scratch (addresses are baked into the session's CUDA graph)
+    // real-state loop (xupdate_real.cu): c_k and m_{k-1} on the sampled locations, and a second v buffer so that the last
+    // x-update still finds v_{K-2}
+    bool lean = false;
+    int lean_group = 0;       // slices per forward / solve / adjoint triple (sized so that v is re-read from L2)
+    DevBuf v_alt, cstate, mprev;
     float *h_in = nullptr, *h_out = nullptr;  // pinned, host-callback path
     bool uploaded = false;
     // one steady-state ADMM iteration (x-update, min/max, 64-conv denoiser = ~130 launches) captured as a CUDA graph:
@@ -804,6 +820,8 @@ struct qmri_admm {
     int64_t graph_launches = 0;
     bool graph_failed = false;
 };
+
+static bool admm_lean_eligible(const qmri_op* op, int S);
 
 extern "C" int qmri_admm_create(qmri_op* op, int S, const qmri_admm_params* params, qmri_admm** out) {
     if (!op || !params || !out) return qmri_fail(QMRI_EINVAL, "qmri_admm_create: null argument");
@@ -829,6 +847,23 @@ extern "C" int qmri_admm_create(qmri_op* op, int S, const qmri_admm_params* para
     r |= st->w_re.ensure(n * 4);  r |= st->w_im.ensure(n * 4);
     r |= st->x_re.ensure(n * 4);  r |= st->x_im.ensure(n * 4);
     r |= st->v.ensure(n * 4);
+    st->lean = admm_lean_eligible(op, S);
+    if (getenv("QMRI_DEBUG"))
+        fprintf(stderr, "libqmri_b200: admm session S = %d: %s-state x-update (general %d, stream_ok %d, real_ok %d, ns_max %d, r_n_ovf %d)\n", S,
+                st->lean ? "real" : "complex", (int)op->general, (int)op->t.stream_ok, (int)op->t.real_ok, op->t.ns_max, op->t.r_n_ovf);
+    if (st->lean) {
+        const char* env = getenv("QMRI_K1R_GROUP");  // tuning knob: slices per kernel triple
+        st->lean_group = std::max(1, std::min(S, env ? atoi(env) : 24));
+        const size_t ns = (size_t)op->t.ns_max;
+        r |= st->v_alt.ensure(n * 4);
+        r |= st->cstate.ensure(k1r_state_elems(S, op->C, (int)ns) * sizeof(float2));
+        r |= st->mprev.ensure(k1r_state_elems(S, op->C, (int)ns) * sizeof(float2));
+        // scratch of both kernel families, sized once (their addresses end up in the captured graph)
+        const size_t part_c = k1_stream_part_elems(S, op->C, k1_stream_groups(S, op->C, ctx->sm_count), (int)ns);
+        const size_t part_r = k1r_part_elems(st->lean_group, op->C, 8, (int)ns);
+        r |= st->k1_part.ensure(std::max(part_c, part_r) * sizeof(float2));
+        r |= st->k1_cbuf.ensure(k1_stream_cbuf_elems(S, op->C, (int)ns) * sizeof(float2));
+    }
     r |= st->mm_ord.ensure(2 * S * sizeof(int));
     r |= st->mm_f.ensure(2 * S * sizeof(float));
     if (params->multi_level) r |= st->noise.ensure(hw * 4);
@@ -870,6 +905,7 @@ extern "C" int qmri_admm_destroy(qmri_admm* st) {
     st->y.release(); st->x0_re.release(); st->x0_im.release(); st->w_re.release(); st->w_im.release();
     st->v.release(); st->x_re.release(); st->x_im.release(); st->mm_ord.release(); st->mm_f.release();
     st->noise.release(); st->cb_in.release(); st->cb_out.release(); st->k1_part.release(); st->k1_cbuf.release();
+    st->v_alt.release(); st->cstate.release(); st->mprev.release();
     if (st->h_in) cudaFreeHost(st->h_in);
     if (st->h_out) cudaFreeHost(st->h_out);
     if (st->graph) cudaGraphExecDestroy(st->graph);
@@ -896,6 +932,11 @@ extern "C" int qmri_admm_upload(qmri_admm* st, const void* y, int y_dtype, const
     // w starts as X0 so that qmri_admm_xupdate_only (profiling) has a defined state before the first qmri_admm_run
     QCUDA(cudaMemcpyAsync(st->w_re.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     QCUDA(cudaMemcpyAsync(st->w_im.p, st->x0_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (st->lean) {  // the same for the real-state loop: v = Re X0, c = m = 0
+        QCUDA(cudaMemcpyAsync(st->v.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        QCUDA(cudaMemsetAsync(st->cstate.p, 0, st->cstate.bytes, ctx->stream));
+        QCUDA(cudaMemsetAsync(st->mprev.p, 0, st->mprev.bytes, ctx->stream));
+    }
     st->uploaded = true;
     return QMRI_OK;
 }
@@ -919,7 +960,125 @@ static int admm_k1(qmri_admm* st, bool write_x) {
     return k1_dispatch(op, p, st->S, &st->k1_part, &st->k1_cbuf);
 }
 
-static int admm_denoise(qmri_admm* st) {
+// ---- real-state loop (xupdate_real.cu) ---------------------------------------------------------------------------------
+// Used when the streaming kernels would run anyway (two slices or more), V is the identity and the mask fits the folded
+// work-item tables; QMRI_K1_STATE=complex forces the complex-state kernels (tests compare the two).
+static bool admm_lean_eligible(const qmri_op* op, int S) {
+    const char* env = getenv("QMRI_K1_STATE");
+    if (env && !strcmp(env, "complex")) return false;
+    if (op->general || !op->t.stream_ok || !op->t.real_ok || op->k1_kernel == 1) return false;
+    if (!k1r_fits(op->t.ns_max, op->t.r_n_ovf)) return false;
+    return op->k1_kernel == 2 || (long long)S * op->C * K1_STREAM_MIN_IMAGES_DIV >= (long long)op->ctx->sm_count;
+}
+
+static void admm_lean_params(const qmri_admm* st, K1RealParams& p, int s0) {
+    const qmri_op* op = st->op;
+    const size_t ns = (size_t)op->t.ns_max, sc = (size_t)s0 * op->C * ns;
+    p.y = st->y.as<float2>() + (size_t)s0 * op->t.nmeas;
+    p.cstate = st->cstate.as<float2>() + sc;
+    p.mprev = st->mprev.as<float2>() + sc;
+    p.cbuf = st->k1_cbuf.as<float2>() + sc;
+    p.part = st->k1_part.as<float2>();
+    p.minmax = st->mm_ord.as<int>() + 2 * s0;
+    p.frame_ptr = op->d_frame_ptr;
+    p.tw2 = op->d_tw2;
+    p.tw448 = op->d_tw448;
+    p.itA = op->d_ritA;
+    p.itB = op->d_ritB;
+    p.ent = op->d_rent;
+    p.rowmask = op->d_rrowmask;
+    p.n_ovf = op->t.r_n_ovf;
+    p.C = op->C;
+    p.nmeas = op->t.nmeas;
+    p.ns_max = op->t.ns_max;
+    p.inv_1p_rho = (float)(1.0 / (1.0 + st->prm.gamma));
+}
+
+// steady state: out = v + Re(A^H c'), c' from the recurrence; slice groups keep v in L2 between the forward and adjoint kernels
+static int admm_k1_lean(qmri_admm* st, const float* v, float* out) {
+    qmri_op* op = st->op;
+    qmri_ctx* ctx = op->ctx;
+    const size_t img = op->plane();
+    const float half_inv_n = 0.5f / (float)op->N;
+    for (int s0 = 0; s0 < st->S; s0 += st->lean_group) {
+        const int sg = std::min(st->lean_group, st->S - s0);
+        K1RealParams p = {};
+        admm_lean_params(st, p, s0);
+        p.v = v + (size_t)s0 * img;
+        p.out = out + (size_t)s0 * img;
+        p.G = k1r_groups(sg, op->C, ctx->sm_count);
+        p.rec = 1;
+        p.part_scale = half_inv_n;
+        p.cbuf_scale = half_inv_n;
+        QCHECK(k1r_forward(ctx, p, sg));
+        QCHECK(k1r_solve(ctx, p, sg));
+        QCHECK(k1r_adjoint(ctx, p, sg));
+    }
+    return QMRI_OK;
+}
+
+// first x-update (PnP_ADMM.m:102 with v = X0, u = 0): w_1 = X0 + A^H c_1, c_1 = (y - A X0) / (1 + rho); X0 is complex, so the
+// complex streaming kernels do the transforms and the recurrence kernel keeps m_0 = A X0 and c_1
+static int admm_k1_lean_first(qmri_admm* st) {
+    qmri_op* op = st->op;
+    qmri_ctx* ctx = op->ctx;
+    K1Params p = {};
+    k1_fill_tables(op, p);
+    p.mode = K1_SOLVE;
+    p.in_re = st->x0_re.as<float>();
+    p.in_im = st->x0_im.as<float>();
+    p.out_re = st->w_re.as<float>();
+    p.out_im = st->w_im.as<float>();
+    p.y = st->y.as<float2>();
+    p.minmax = st->mm_ord.as<int>();
+    p.inv_1p_rho = (float)(1.0 / (1.0 + st->prm.gamma));
+    p.rho = st->prm.gamma;
+    p.stage = K1_STAGE_FWD_ONLY | K1_STAGE_NO_SOLVE;
+    QCHECK(k1_dispatch(op, p, st->S, &st->k1_part, &st->k1_cbuf));
+    K1RealParams r = {};
+    admm_lean_params(st, r, 0);
+    r.G = k1_stream_groups(st->S, op->C, ctx->sm_count);  // the layout the complex forward kernel left in `part`
+    r.rec = 0;
+    r.part_scale = 1.0f / (float)op->N;
+    r.cbuf_scale = 1.0f / (float)op->N;
+    QCHECK(k1r_solve(ctx, r, st->S));
+    p.stage = K1_STAGE_ADJ_ONLY;
+    return k1_dispatch(op, p, st->S, &st->k1_part, &st->k1_cbuf);
+}
+
+// last x-update: the complex iterate x_K = 2 v_{K-1} - base + A^H (c_K - c_{K-1}), base = v_{K-2} (or X0 when K = 2)
+static int admm_k1_lean_last(qmri_admm* st, const float* vcur, const float* base_re, const float* base_im) {
+    qmri_op* op = st->op;
+    qmri_ctx* ctx = op->ctx;
+    const size_t img = op->plane();
+    for (int s0 = 0; s0 < st->S; s0 += st->lean_group) {
+        const int sg = std::min(st->lean_group, st->S - s0);
+        K1RealParams r = {};
+        admm_lean_params(st, r, s0);
+        r.v = vcur + (size_t)s0 * img;
+        r.G = k1r_groups(sg, op->C, ctx->sm_count);
+        r.rec = 2;
+        r.part_scale = 0.5f / (float)op->N;
+        r.cbuf_scale = 1.0f / (float)op->N;  // the complex inverse transform takes c as it is
+        QCHECK(k1r_forward(ctx, r, sg));
+        QCHECK(k1r_solve(ctx, r, sg));
+    }
+    QCHECK(k1r_last_base(ctx, vcur, base_re, base_im, st->x_re.as<float>(), st->x_im.as<float>(), img * st->S));
+    K1Params p = {};
+    k1_fill_tables(op, p);
+    p.mode = K1_SOLVE;
+    p.in_re = st->x_re.as<float>();
+    p.in_im = st->x_im.as<float>();
+    p.out_re = st->x_re.as<float>();  // in place: every thread reads the elements it writes
+    p.out_im = st->x_im.as<float>();
+    p.y = st->y.as<float2>();
+    p.inv_1p_rho = (float)(1.0 / (1.0 + st->prm.gamma));
+    p.rho = st->prm.gamma;
+    p.stage = K1_STAGE_ADJ_ONLY;
+    return k1_dispatch(op, p, st->S, &st->k1_part, &st->k1_cbuf);
+}
+
+static int admm_denoise(qmri_admm* st, float* v_out) {
     qmri_op* op = st->op;
     qmri_ctx* ctx = op->ctx;
     const int S = st->S;
@@ -927,7 +1086,7 @@ static int admm_denoise(qmri_admm* st) {
     const float* mm = st->mm_f.as<float>();
     if (st->prm.net) {
         // planes are MATLAB-ordered: rows = m (M of them), fastest extent = N
-        return unetres_forward_dev(st->prm.net, st->w_re.as<float>(), st->v.as<float>(), mm,
+        return unetres_forward_dev(st->prm.net, st->w_re.as<float>(), v_out, mm,
                                    st->prm.multi_level ? st->noise.as<float>() : nullptr, S, op->M, op->N, 1);
     }
     // callback path: v_in = (Re w - min)/range [, noise map]; v = f(v_in) * range + min
@@ -951,7 +1110,7 @@ static int admm_denoise(qmri_admm* st) {
         if (rc == 0) QCUDA(cudaMemcpyAsync(st->cb_out.p, st->h_out, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (rc != 0) return qmri_fail(QMRI_ECALLBACK, "denoiser callback returned %d", rc);
-    return normalize_planar(ctx, st->cb_out.as<float>(), st->v.as<float>(), mm, hw * 10, S, 1);
+    return normalize_planar(ctx, st->cb_out.as<float>(), v_out, mm, hw * 10, S, 1);
 }
 
 extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
@@ -967,8 +1126,23 @@ extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
     QCUDA(cudaMemcpyAsync(st->x_re.p, st->x0_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     QCUDA(cudaMemcpyAsync(st->x_im.p, st->x0_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     QCHECK(k1_minmax_init(ctx, st->mm_ord.as<int>(), S));
+    const bool lean = st->lean;
     auto iteration = [&](int k) -> int {
-        if (k == 0) {
+        // real-state loop: the denoiser output of the second-to-last iteration goes to a second buffer, because the last
+        // x-update needs v_{K-2} next to v_{K-1}
+        float* v_out = (lean && k == iters - 2) ? st->v_alt.as<float>() : st->v.as<float>();
+        if (k == 0 && lean) {
+            QCHECK(admm_k1_lean_first(st));
+            if (iters == 1) {  // x_1 is the result
+                QCUDA(cudaMemcpyAsync(st->x_re.p, st->w_re.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                QCUDA(cudaMemcpyAsync(st->x_im.p, st->w_im.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        } else if (lean && k == iters - 1) {
+            QCHECK(admm_k1_lean_last(st, st->v_alt.as<float>(), k == 1 ? st->x0_re.as<float>() : st->v.as<float>(),
+                                     k == 1 ? st->x0_im.as<float>() : nullptr));
+        } else if (lean) {
+            QCHECK(admm_k1_lean(st, st->v.as<float>(), st->w_re.as<float>()));
+        } else if (k == 0) {
             // Iteration 1 of PnP_ADMM.m:102 with v = X0, u = 0: x_1 = argmin |y - A x|^2 + rho |x - X0|^2, w_1 = x_1 + u_0 = x_1.
             // (For X0 = A^H y and A A^H = I this returns X0 itself - the reference driver's case - but param.X0 is the caller's.)
             K1Params p = {};
@@ -995,14 +1169,14 @@ extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
         if (k == iters - 1) return QMRI_OK;
         minmax_finalize_kernel<<<nblk(S, 128), 128, 0, ctx->stream>>>(st->mm_ord.as<int>(), st->mm_f.as<float>(), S);
         QLAUNCH_CHECK(ctx);
-        return admm_denoise(st);
+        return admm_denoise(st, v_out);
     };
     // Iterations 2 .. iters-2 launch the same kernels with the same arguments: capture one and replay it.  Iterations 0 and 1
     // run directly first, so every lazy initialisation (workspaces, tensor maps, function attributes) is done before capture.
     qmri_net* net = st->prm.net;
     const bool want_graph = net && !st->graph_failed && iters >= 6 && !getenv("QMRI_NO_GRAPH") && !getenv("QMRI_PROFILE") && !getenv("QMRI_TC_TRACE");
     for (int k = 0; k < iters; ++k) {
-        if (!(want_graph && k >= 2 && k < iters - 1)) {
+        if (!(want_graph && k >= 2 && k < iters - (lean ? 2 : 1))) {
             QCHECK(iteration(k));
             continue;
         }
@@ -1048,9 +1222,14 @@ extern "C" int qmri_admm_run(qmri_admm* st, int iters) {
 extern "C" int qmri_admm_xupdate_only(qmri_admm* st, int reps) {
     if (!st || !st->uploaded) return qmri_fail(QMRI_EINVAL, "qmri_admm_xupdate_only: state not ready");
     DevSetter ds(st->op->ctx->device);
-    for (int i = 0; i < reps; ++i) QCHECK(admm_k1(st, false));
+    for (int i = 0; i < reps; ++i) {
+        if (st->lean) QCHECK(admm_k1_lean(st, st->v.as<float>(), st->w_re.as<float>()));
+        else QCHECK(admm_k1(st, false));
+    }
     return QMRI_OK;
 }
+
+extern "C" int qmri_admm_xupdate_bytes(qmri_admm* st) { return st ? (st->lean ? 8 : 20) : 0; }
 
 extern "C" int qmri_admm_download(qmri_admm* st, void* x_out, int x_dtype) {
     if (!st || !x_out) return qmri_fail(QMRI_EINVAL, "qmri_admm_download: null argument");

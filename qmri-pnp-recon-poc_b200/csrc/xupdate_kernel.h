@@ -8,7 +8,7 @@ struct qmri_ctx;
 constexpr int K1_PHASES = 8;  // == optab::K1_PHASES
 
 enum { K1_ADMM = 0, K1_SOLVE = 1, K1_FORWARD = 2, K1_ADJOINT = 3 };
-enum { K1_STAGE_FWD_ONLY = 1, K1_STAGE_ADJ_ONLY = 2 };
+enum { K1_STAGE_FWD_ONLY = 1, K1_STAGE_ADJ_ONLY = 2, K1_STAGE_NO_SOLVE = 4 };
 
 struct K1Params {
     // planar fp32 images [S][C][M][N] (n fastest - the MATLAB layout of an N x M x C x S array)
@@ -60,6 +60,41 @@ size_t k1_stream_part_elems(int S, int C, int G, int ns_max);
 size_t k1_stream_cbuf_elems(int S, int C, int ns_max);
 int k1_stream_launch(qmri_ctx* ctx, const K1Params& p, int S, int ns_max);
 int k1_minmax_init(qmri_ctx* ctx, int* minmax, int S);
+
+// real-image variant of the streaming kernels (xupdate_real.cu): the PnP-ADMM loop with only real images crossing HBM
+struct K1RealParams {
+    const float* v;          // [S][C][M][N] real image: transformed by the forward kernel, added to by the adjoint kernel
+    float* out;              // [S][C][M][N] v + Re(A^H c)
+    const float2* y;         // [S][nmeas]
+    float2* cstate;          // [S][C][ns_max] c_k (unscaled), updated in place
+    float2* mprev;           // [S][C][ns_max] m_{k-1} = A v_{k-1}, updated in place
+    float2* part;            // [S][C][G][ns_max] partial sample sums of the forward kernel
+    float2* cbuf;            // [S][C][ns_max] input of the inverse transform (pre-scaled)
+    int* minmax;             // optional [S][2] ordered-int min / max of out
+    const int* frame_ptr;    // [C+1]
+    const float2* tw2;       // [16][16]
+    const float2* tw448;     // [448]
+    const uint32_t* itA;     // [C][224] folded-row work items (K1Tables::r_itA)
+    const uint32_t* itB;
+    const uint32_t* ent;     // [nmeas] j | k2' << 16 | conj << 31
+    const uint16_t* rowmask; // [C][16] symmetric row mask
+    int n_ovf;
+    int G;                   // slab groups (CTAs) per image of `part`: 1, 2, 4 or 8 (8 slabs of 28 real columns)
+    int slabs_per_cta;       // set by the launchers
+    int C, nmeas, ns_max;
+    int rec;                 // stream_solver_kernel: 0 first x-update, 1 steady state, 2 last x-update
+    float part_scale;        // what the summed partials are multiplied by to give m = A v
+    float cbuf_scale;        // what c is multiplied by on its way into the inverse transform
+    float inv_1p_rho;
+};
+int k1r_groups(int S, int C, int sm_count);
+size_t k1r_part_elems(int S, int C, int G, int ns_max);
+size_t k1r_state_elems(int S, int C, int ns_max);
+bool k1r_fits(int ns_max, int n_ovf);
+int k1r_forward(qmri_ctx* ctx, const K1RealParams& p, int S);
+int k1r_solve(qmri_ctx* ctx, const K1RealParams& p, int S);
+int k1r_adjoint(qmri_ctx* ctx, const K1RealParams& p, int S);
+int k1r_last_base(qmri_ctx* ctx, const float* v, const float* base_re, const float* base_im, float* x_re, float* x_im, size_t n);
 
 // general V: the per-location kernels that mix channels around the streaming transforms (xupdate_general.cu)
 struct GeneralMix {

@@ -377,6 +377,164 @@ QHD void p4_item_spill(float2* o, const float2 (&SP)[NP_STREAM], const float2 (&
     }
 }
 
+// =====================================================================================
+// Real-image variant (xupdate_real.cu): in the loop the transforms only ever see REAL images -
+//   forward   m = A v            (v = denoiser output, real)
+//   inverse   Re(A^H c)          (only the real part of w = v + A^H c feeds the denoiser)
+// so two real columns (m, m+1) ride through one complex length-224 FFT:
+//   forward: Z = FFT_n(v[:, m] + i v[:, m+1]);  T_m(k1) = (Z(k1) + conj Z(-k1)) / 2,  T_{m+1}(k1) = (Z(k1) - conj Z(-k1)) / (2i)
+//   inverse: Re IFFT2(C) = IFFT2(C_h), C_h(k) = (C(k) + conj C(-k)) / 2 Hermitian, so U_h(k1, m) is Hermitian in k1 for every m
+//            and IFFT_n(U_h(., m) + i U_h(., m+1)) = column m + i column m+1.
+// A slab is 14 packed columns = 28 real columns; the sparse sums take it as two half slabs of 7 packed = 14 real columns.
+// Work items cover FOLDED rows k1 <= 112 (op_tables.h): a sample of row 224 - k1 enters row k1 as (224 - k2) mod 224 with its
+// value conjugated - T(224 - k1, m) = conj T(k1, m) - so one item serves both rows from the same registers.
+// Entry word: j | k2' << 16 | conj << 31.  Scaling: the forward sums come out 2 x too large (the 1/2 of T is left to the solve
+// kernel) and the inverse expects c already multiplied by 1/2 (the 1/2 of C_h).
+// =====================================================================================
+constexpr int HP_REAL = 7;        // packed columns per half slab
+
+// forward: pc[j] += sum over the 28 real columns of the slab starting at real column m0 of  2 T_m(k1) e^{-2 pi i k2 m / 224}
+QHD void p3r_item(const float2* ws, int k1, const uint32_t* ent, int cnt, const float2* tw448, int m0, float2* pc) {
+    if (cnt == 0) return;
+    const int k1n = k1 ? NF - k1 : 0;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        // 2 T_a = Z(k1) + conj Z(-k1),  2 T_b = (Z(k1) - conj Z(-k1)) / i;  mirrored about packed column 3 of the half slab
+        float2 Ea[4], Em[4], Oa[4], Om[4];  // [0]: centre value in Ea / Oa; [d]: sums (a) and differences (m) of columns 3 + d, 3 - d
+        {
+            float2 ta[HP_REAL], tb[HP_REAL];
+#pragma unroll
+            for (int j = 0; j < HP_REAL; ++j) {
+                const float2 zp = ws[(HP_REAL * h + j) * CS + k1], zn = ws[(HP_REAL * h + j) * CS + k1n];
+                ta[j] = make_float2(zp.x + zn.x, zp.y - zn.y);
+                tb[j] = make_float2(zp.y + zn.y, zn.x - zp.x);
+            }
+            Ea[0] = ta[3];
+            Oa[0] = tb[3];
+            Em[0] = Om[0] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int d = 1; d < 4; ++d) {
+                Ea[d] = cadd(ta[3 + d], ta[3 - d]);
+                Em[d] = csub(ta[3 + d], ta[3 - d]);
+                Oa[d] = cadd(tb[3 + d], tb[3 - d]);
+                Om[d] = csub(tb[3 + d], tb[3 - d]);
+            }
+        }
+        const int mh = m0 + 14 * h;
+        for (int q = 0; q < cnt; ++q) {
+            const uint32_t en = ent[q];
+            const int k2 = (int)((en >> 16) & 0xffu), j = (int)(en & 0xffffu);
+            const float2 wk = tw448[2 * k2];                           // e^{-i phi}, phi = 2 pi k2 / 224
+            const float2 r1 = cmul(wk, wk);                            // e^{-2 i phi}: one packed column
+            const float2 tc = tw448[(2 * k2 * (mh + 6)) % (2 * NF)];   // e^{-i phi (mh + 6)}: packed column 3 = real column mh + 6
+            float2 r = r1;
+            float ex = Ea[0].x, ey = Ea[0].y, ox = Oa[0].x, oy = Oa[0].y;
+#pragma unroll
+            for (int d = 1; d < 4; ++d) {
+                ex = fmaf(r.x, Ea[d].x, ex);
+                ex = fmaf(-r.y, Em[d].y, ex);
+                ey = fmaf(r.x, Ea[d].y, ey);
+                ey = fmaf(r.y, Em[d].x, ey);
+                ox = fmaf(r.x, Oa[d].x, ox);
+                ox = fmaf(-r.y, Om[d].y, ox);
+                oy = fmaf(r.x, Oa[d].y, oy);
+                oy = fmaf(r.y, Om[d].x, oy);
+                if (d < 3) r = cmul(r, r1);
+            }
+            const float2 o = cmul(make_float2(ox, oy), wk);            // the odd real column of a pair sits one column further
+            float2 a = cmul(make_float2(ex + o.x, ey + o.y), tc);
+            if (en & 0x80000000u) a.y = -a.y;                          // sample of row 224 - k1: conj of the sum for (k1, -k2)
+            const float2 pv = pc[j];
+            pc[j] = make_float2(pv.x + a.x, pv.y + a.y);
+        }
+    }
+}
+
+// inverse, step 1 (one half slab of 14 real columns starting at mh): like p4_item_partial with the folded entries
+QHD void p4r_item_partial(float2 (&SP)[NP_STREAM], float2 (&SM)[NP_STREAM], const uint32_t* ent, int cnt, const float2* tw448, int mh,
+                          const float2* pc) {
+#pragma unroll
+    for (int d = 0; d < NP_STREAM; ++d) {
+        SP[d] = make_float2(0.f, 0.f);
+        SM[d] = make_float2(0.f, 0.f);
+    }
+    for (int q = 0; q < cnt; ++q) {
+        const uint32_t en = ent[q];
+        const int k2 = (int)((en >> 16) & 0xffu), j = (int)(en & 0xffffu);
+        float2 r = tw448[k2];
+        const float2 st = cmul(r, r);
+        const float2 tc = tw448[(k2 * (2 * mh + 13)) % (2 * NF)];
+        float2 cv = pc[j];
+        if (en & 0x80000000u) cv.y = -cv.y;
+        const float2 u = cmul(cv, make_float2(tc.x, -tc.y));
+#pragma unroll
+        for (int d = 0; d < NP_STREAM; ++d) {
+            SP[d].x = fmaf(u.x, r.x, SP[d].x);
+            SP[d].y = fmaf(u.y, r.x, SP[d].y);
+            SM[d].x = fmaf(u.x, r.y, SM[d].x);
+            SM[d].y = fmaf(u.y, r.y, SM[d].y);
+            r = cmul(r, st);
+        }
+    }
+}
+// inverse, step 2: leave the (P, M) basis, pack real column pairs (a, b) = (2 j, 2 j + 1) of the half slab as
+//   Zp_j(k1) = G_a + i G_b,   Zp_j(-k1) = conj G_a + i conj G_b      (G = the folded row's partial U_h)
+// and store (ACC = false: primary item) or add (ACC = true: overflow partials) rows k1 and 224 - k1 of packed columns 7 h + j.
+// Rows 0 and 112 are their own mirror: both contributions land on the same element.
+template <bool ACC>
+QHD void p4r_store(float2* ws, int k1, int h, const float2 (&SP)[NP_STREAM], const float2 (&SM)[NP_STREAM]) {
+    const int k1n = k1 ? NF - k1 : 0;
+    float2 G[2 * NP_STREAM];
+#pragma unroll
+    for (int d = 0; d < NP_STREAM; ++d) {
+        G[7 + d] = make_float2(SP[d].x + SM[d].y, SP[d].y - SM[d].x);   // u conj(r)
+        G[6 - d] = make_float2(SP[d].x - SM[d].y, SP[d].y + SM[d].x);   // u r
+    }
+#pragma unroll
+    for (int j = 0; j < HP_REAL; ++j) {
+        const float2 a = G[2 * j], b = G[2 * j + 1];
+        float2 zp = make_float2(a.x - b.y, a.y + b.x);
+        const float2 zn = make_float2(a.x + b.y, b.x - a.y);
+        float2* colp = ws + (HP_REAL * h + j) * CS;
+        if (k1n == k1) {
+            zp = make_float2(zp.x + zn.x, zp.y + zn.y);
+            if (ACC) {
+                const float2 o = colp[k1];
+                zp = make_float2(o.x + zp.x, o.y + zp.y);
+            }
+            colp[k1] = zp;
+        } else {
+            if (ACC) {
+                const float2 o = colp[k1], on = colp[k1n];
+                colp[k1] = make_float2(o.x + zp.x, o.y + zp.y);
+                colp[k1n] = make_float2(on.x + zn.x, on.y + zn.y);
+            } else {
+                colp[k1] = zp;
+                colp[k1n] = zn;
+            }
+        }
+    }
+}
+// the row's overflow partials, summed in slot order, then added through the same packing
+QHD void p4r_row_add_overflow(float2* ws, int k1, int h, const float2* ovf, int novf, int stride) {
+    float2 SP[NP_STREAM], SM[NP_STREAM];
+#pragma unroll
+    for (int d = 0; d < NP_STREAM; ++d) {
+        SP[d] = ovf[d];
+        SM[d] = ovf[NP_STREAM + d];
+    }
+    for (int i = 1; i < novf; ++i) {
+        const float2* o = ovf + (size_t)i * stride;
+#pragma unroll
+        for (int d = 0; d < NP_STREAM; ++d) {
+            const float2 a = o[d], b = o[NP_STREAM + d];
+            SP[d].x += a.x; SP[d].y += a.y;
+            SM[d].x += b.x; SM[d].y += b.y;
+        }
+    }
+    p4r_store<true>(ws, k1, h, SP, SM);
+}
+
 // item table words (op_tables.h): A = k1 | cnt << 8 | start << 16 (k1 == 255: no item);
 //                                 B = slot | novf << 8 | ovf0 << 16 (slot 0: primary; bits 24-31 unused: rows without samples are
 //                                     skipped by the inverse FFT through the row mask)

@@ -308,7 +308,7 @@ int launch_mode(qmri_ctx* ctx, const K1Params& p, int S) {
     if (MODE != K1_ADJOINT && !(p.stage & K1_STAGE_ADJ_ONLY)) {
         stream_fwd_kernel<MODE><<<dim3(p.G, p.C, S), THREADS, sf, ctx->stream>>>(p);
         QLAUNCH_CHECK(ctx);
-        if (!p.shared_mask) {
+        if (!p.shared_mask && !(p.stage & K1_STAGE_NO_SOLVE)) {  // (the real-state loop runs its own recurrence on the partial sums)
             stream_solve_kernel<MODE><<<dim3(p.C, S), 256, 0, ctx->stream>>>(p);
             QLAUNCH_CHECK(ctx);
         }

@@ -144,6 +144,10 @@ class AdmmSession:
     def xupdate_only(self, reps=1):
         check(self.lib.qmri_admm_xupdate_only(self.handle, int(reps)))
 
+    def xupdate_bytes(self):
+        """Algorithmic bytes per pixel-channel of one x-update in the state formulation this session runs (8 or 20)."""
+        return int(self.lib.qmri_admm_xupdate_bytes(self.handle))
+
     def download(self, out=None):
         F = self.F
         x = out if out is not None else np.zeros((F.N, F.M, F.C, self.S), np.complex128, order="F")

@@ -108,3 +108,35 @@ def test_general_V_host_tables(emu, pat, arg, L, C):
     for u in rng.choice(len(U), size=40, replace=False):
         G = sum(np.outer(V[i], V[i]) for i in member[int(U[u])])
         assert np.allclose(Minv[u], np.linalg.inv(G + rho * np.eye(C)), rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("pat,arg,qmin", [(0, 771.0, "1"), (0, 771.0, "8"), (1, 1 / 65, "8")])
+def test_k1_real_image_kernels(emu, pat, arg, qmin, monkeypatch):
+    """The real-image streaming kernels of the loop (csrc/xupdate_real.cu: two real columns per complex FFT, folded k-space rows,
+    Hermitian-packed inverse) thread by thread on the CPU: m = A v and v + Re(A^H c) against the float64 oracle."""
+    monkeypatch.setenv("QMRI_K1_QMIN", qmin)
+    emu.k1emu_run_real.restype = ctypes.c_int
+    emu.k1emu_run_real.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int] + [fp] * 5 + [ctypes.POINTER(ctypes.c_int)]
+    C = 3
+    Po = (sampling.setup_subsampling_spiralgrided(224, 224, 771, np.eye(C)) if pat == 0
+          else sampling.setup_subsampling_epi(224, 224, 1 / 65, np.eye(C)))
+    F = sampling.FOperator(Po)
+    n = Po.nmeas
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((224, 224, C))
+    vr, _ = planar(v + 0j)
+    yout = np.zeros((n, 2), np.float32)
+    novf = ctypes.c_int(-1)
+    assert emu.k1emu_run_real(0, pat, arg, C, 1, P(vr), None, None, P(yout), None, ctypes.byref(novf)) == n
+    assert 0 <= novf.value <= 96
+    assert rel_l2(yout[:, 0] + 1j * yout[:, 1], F.forward(v)) < 1e-6
+    c = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    c32 = np.stack([c.real, c.imag], 1).astype(np.float32)
+    out = np.zeros_like(vr)
+    mm = np.zeros(2, np.float32)
+    emu.k1emu_run_real(1, pat, arg, C, 1, P(vr), P(c32), P(out), None, P(mm), None)
+    corr = np.real(F.adjoint(c))
+    got = np.transpose(out.astype(np.float64), (2, 1, 0))
+    assert rel_l2(got - v, corr) < 2e-6          # the correction itself
+    assert rel_l2(got, v + corr) < 1e-6
+    assert abs(mm[0] - (v + corr).min()) < 1e-5 and abs(mm[1] - (v + corr).max()) < 1e-5
