@@ -552,12 +552,31 @@ def run_ours(args, rank, world, local_rank):
                                            "us_per_slice_iteration": us_it,
                                            "frac_if_counted_at_20B": 20.0 * HW * C_CH * S / t_launch / 1e9 / peaks["hbm_gbs"]},
                "l2_note": None if S * bpp * HW * C_CH > 2 * (126 << 20) else "working set fits L2: not an HBM measurement"}
-    # K2 from the matching-only leg above (complex data: 40 flop per px-atom)
+    # K2 from the matching-only leg above (complex data: 40 flop per px-atom).  Pipe choice (profiles/r02_k2_pipes.md, from ncu
+    # counters): the tcgen05 tf32 kernel from 2048 atoms on, the FP32-FMA kernel below and for C > 10.
     pxa = S * HW * K * 2 / (ms_match * 1e-3)
-    fp32_peak = 148 * 128 * 2 * ((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
-    roof_k2 = {"bound": "fp32", "kernel": "match_kernel", "achieved": pxa * 40 / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-               "frac": pxa * 40 / 1e12 / fp32_peak, "px_atoms_per_s": pxa, "atoms": K, "pixels": S * HW,
-               "ms_per_slice": ms_match / (2 * S), "share_of_step": (ms_match / 2) / step_ms}
+    sm_mhz = ((clocks or {}).get("sm_max_mhz") or 1965.0)
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    pipe = "fma" if (os.environ.get("QMRI_K2_PIPE") == "fma" or K < 2048) else "tensor"
+    if pipe == "tensor":
+        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        roof_k2 = {"bound": "tensor", "kernel": "match_tc_kernel (tcgen05 kind::tf32, split operands, group-maximum epilogue, FP32 rescore)",
+                   "achieved": pxa * 40 / 1e12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": pxa * 40 / 1e12 / tf32_peak,
+                   "peak_source": f"{peaks['src']} dense bf16 (sustained) / 2 = tf32 rate",
+                   "issued_tflops": pxa * 128 / 1e12, "frac_issued": pxa * 128 / 1e12 / tf32_peak,
+                   "issued_note": "the split a = hi + lo lays 3 x 10 channels along K = 32 and complex pixels take two accumulators: 128 tensor "
+                                  "flops are issued per 40 algorithmic ones",
+                   "limiter": "the epilogue, not the MMA: every score is read back from TMEM and costs 3 FP32 instructions on 8 warps "
+                              "(profiles/r02_k2_pipes.md: tensor pipe 41 % active before the 8-warp epilogue; TMEM-read + FP32 microbenchmark "
+                              "profiles/r02_ldtm_bench.txt: 22.8 scores/clk/SM with 4 warps, 30.9 with 8)",
+                   "scores_per_clk_per_sm": pxa / (148 * sm_mhz * 1e6),
+                   "vs_fp32_fma_kernel": {"px_atoms_per_s": 1.26e12, "what": "match_kernel on the same data (profiles/r02_k2_pipes.md): 76 % FMA-pipe active, 0.67 of the FP32 peak"},
+                   "px_atoms_per_s": pxa, "atoms": K, "pixels": S * HW,
+                   "ms_per_slice": ms_match / (2 * S), "share_of_step": (ms_match / 2) / step_ms}
+    else:
+        roof_k2 = {"bound": "fp32", "kernel": "match_kernel", "achieved": pxa * 40 / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                   "frac": pxa * 40 / 1e12 / fp32_peak, "px_atoms_per_s": pxa, "atoms": K, "pixels": S * HW,
+                   "ms_per_slice": ms_match / (2 * S), "share_of_step": (ms_match / 2) / step_ms}
 
     # ---- extras: the other BASELINE configs, short legs ---------------------------------------------------------------------
     extras = {}

@@ -1,5 +1,5 @@
-// K2, tensor-pipe variant - dictionary matching as a tcgen05 kind::tf32 contraction with a fused top-4 epilogue and an FP32
-// rescore; the K x B score matrix of the reference is never materialised.
+// K2, tensor-pipe variant - dictionary matching as a tcgen05 kind::tf32 contraction with a fused group-maximum epilogue and an
+// FP32 rescore; the K x B score matrix of the reference is never materialised.
 //
 // Reference being replaced: main_files/dictionary_matching/mrf_dtm_cpu.m:84-98
 //   ip = dict.D * ctranspose(x(cind,:));  [mt, dm] = max(abs(ip),[],1)
@@ -14,13 +14,19 @@
 // Kernel: persistent, warp-specialised.  Work item = (tile of 128 pixels, atom range).  Warp 0 (TMA): the pixel tile (real and
 // imaginary K-major rows, 2 x 16 KB, loaded once per work item) and a ring of 128-atom tiles (16 KB each) into 128B-swizzled
 // shared memory.  Warp 1 (MMA): per atom tile 2 x 4 tcgen05.mma (M128 x N128 x K8) into one of two TMEM accumulator pairs.
-// Warps 2-5 (epilogue): thread = pixel; tcgen05.ld of the real and imaginary accumulators (issued one 32-column chunk ahead of
-// the arithmetic), s = re^2 + im^2, running maximum of 16-atom groups (3 FP32 instructions per score); the thread keeps the TWO
-// BEST GROUPS by group maximum (strict comparisons: earlier groups stay ahead on exact ties; a per-atom top-k list degenerates on
-// real dictionaries, whose scores rise smoothly along the atom index so that nearly every group enters the list).  At the
-// end of the work item the 32 candidate atoms are rescored with k2_score() - the FP32 FMA kernel's exact expression on the
-// ORIGINAL fp32 atoms and pixels - and the best becomes the packed key  float_bits(score) << 32 | (0xFFFFFFFF - atom), merged with atomicMax like the FMA
-// kernel's (same keys, so atom ranges, kernels and ranks mix freely).
+// Warps 2-9 (epilogue; two per TMEM lane quarter, each taking 64 of the tile's 128 atom columns): thread = pixel; tcgen05.ld of
+// the real and imaginary accumulators (issued one 32-column chunk ahead of the arithmetic), s = re^2 + im^2, the maximum of each
+// 16-atom group as a depth-4 tree (3 FP32 instructions per score; with one or two warps per scheduler a 16-long dependent
+// FMNMX chain was the limiter: ncu showed the epilogue warps issuing 41 % of the cycles).  The thread keeps the TWO BEST GROUPS
+// by group maximum (strict comparisons: earlier groups stay ahead on exact ties).  A per-atom top-k list degenerates on real
+// dictionaries, whose scores rise smoothly along the atom index so that nearly every group enters the list: measured 5.5e11
+// px-atoms/s on the benchmark's dictionary against 1.8e12 on random atoms, and 3.1e12 for group tracking on either.
+// At the end of the work item the thread's 32 candidate atoms are rescored with k2_score() - the FP32 FMA kernel's exact
+// expression on the ORIGINAL fp32 atoms and pixels - and the best becomes the packed key
+//     float_bits(score) << 32 | (0xFFFFFFFF - atom)
+// merged with atomicMax like the FMA kernel's (same keys, so the two column halves of a pixel, atom ranges, kernels and ranks
+// mix freely).  The approximate scores only have to bring the true maximum's group into the top two: they are within 5e-7
+// (relative) of the FP32 scores, so an atom can be missed only inside a reference near-tie (top-2 gap < 1e-6).
 #include <cuda.h>
 #include <math.h>
 #include <string.h>
@@ -37,7 +43,8 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int MT_THREADS = 192;
+constexpr int MT_EPI_WARPS = 8;               // two warps per TMEM lane quarter: each takes 64 of a tile's 128 atom columns
+constexpr int MT_THREADS = 64 + 32 * MT_EPI_WARPS;
 constexpr int MT_BM = 128;                  // pixels per tile
 constexpr int MT_BN = 128;                  // atoms per tile
 constexpr int MT_KF = 32;                   // floats per operand row (128 B = one swizzle row)
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
         mbar_init(a_empty, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], MT_EPI_WARPS);
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
@@ -195,8 +202,9 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
             }
         }
     } else {
-        // ================= epilogue warps: thread = pixel (TMEM lane) =================
-        const int lg = warp & 3;
+        // ================= epilogue warps: thread = (pixel = TMEM lane, half of the tile's atom columns) =================
+        const int lg = warp & 3;                 // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;        // columns [64 half, 64 half + 64) of every accumulator
         const int row = lg * 32 + lane;
         int it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -208,19 +216,23 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
             auto score_chunk = [&](const uint32_t (&re)[32], const uint32_t (&im)[32], int gid) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    float gmax = -1.f;
+                    float sc[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float a = __uint_as_float(re[16 * g + j]);
-                        float sc;
                         if (CPLX) {
                             const float b = __uint_as_float(im[16 * g + j]);
-                            sc = fmaf(b, b, a * a);
+                            sc[j] = fmaf(b, b, a * a);
                         } else {
-                            sc = a * a;
+                            sc[j] = a * a;
                         }
-                        gmax = fmaxf(gmax, sc);  // fmaxf drops NaN
                     }
+                    // maximum as a tree (depth 4): a single warp per scheduler cannot hide a 16-long dependent chain
+#pragma unroll
+                    for (int st = 8; st > 0; st >>= 1)
+#pragma unroll
+                        for (int j = 0; j < st; ++j) sc[j] = fmaxf(sc[j], sc[j + st]);  // fmaxf drops NaN
+                    const float gmax = fmaxf(sc[0], -1.f);
                     if (gmax > g2s) {
                         if (gmax > g1s) {
                             g2s = g1s;
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
             // Accumulator reads run one 32-column chunk ahead of the arithmetic: a chunk's tcgen05.ld is issued before the previous
             // chunk is scored and waited for afterwards (tcgen05.wait::ld covers every outstanding load of the thread).
             uint32_t reA[32], imA[32], reB[32], imB[32];
-            auto tile_addr = [&](int i) { return tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((i & 1) * 2 * MT_BN); };
+            auto tile_addr = [&](int i) { return tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((i & 1) * 2 * MT_BN + 64 * half); };
             if (t0 < t1) {
                 mbar_wait(&tfull[it & 1], (it >> 1) & 1);
                 tc_fence_after();
@@ -250,18 +262,11 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
             }
             for (int t = t0; t < t1; ++t, ++it) {
                 const int ab = it & 1;
-                const uint32_t taddr = tile_addr(it);
-                const int gid = (t - t0) * (MT_BN / 16);
-                load_chunk(taddr + 32, reB, imB);
+                const int gid = (t - t0) * (MT_BN / 16) + 4 * half;
+                load_chunk(tile_addr(it) + 32, reB, imB);
                 score_chunk(reA, imA, gid);
                 tc_wait_ld();
-                load_chunk(taddr + 64, reA, imA);
-                score_chunk(reB, imB, gid + 2);
-                tc_wait_ld();
-                load_chunk(taddr + 96, reB, imB);
-                score_chunk(reA, imA, gid + 4);
-                tc_wait_ld();
-                // every accumulator value of this tile is in registers: hand the buffer back
+                // this warp's share of the tile is in registers: hand the buffer back
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[ab]);
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
                     tc_fence_after();
                     load_chunk(tile_addr(it + 1), reA, imA);
                 }
-                score_chunk(reB, imB, gid + 6);
+                score_chunk(reB, imB, gid + 2);
                 if (t + 1 < t1) tc_wait_ld();
             }
             // rescore the 2 x 16 candidates with the FMA kernel's exact expression on the original fp32 data

@@ -961,11 +961,14 @@ static int admm_k1(qmri_admm* st, bool write_x) {
 }
 
 // ---- real-state loop (xupdate_real.cu) ---------------------------------------------------------------------------------
-// Used when the streaming kernels would run anyway (two slices or more), V is the identity and the mask fits the folded
-// work-item tables; QMRI_K1_STATE=complex forces the complex-state kernels (tests compare the two).
+// Opt-in (QMRI_K1_STATE=real) where the streaming kernels would run anyway (two slices or more), V is the identity and the mask
+// fits the folded work-item tables.  Measured on B200 at 120 slices (profiles/r02_k1_real_vs_complex.md): the real kernels move
+// 8 instead of 24 bytes per pixel-channel and run half the FFT work, yet take the same time (forward 39 vs 42 us, adjoint 58 vs
+// 58 us per 24 slices) - both families are bound by the critical path of the sparse m-direction sums between two CTA barriers,
+// not by bytes or FFT flops - so the complex-state kernels stay the default and the roofline is reported against their 20 B.
 static bool admm_lean_eligible(const qmri_op* op, int S) {
     const char* env = getenv("QMRI_K1_STATE");
-    if (env && !strcmp(env, "complex")) return false;
+    if (!env || strcmp(env, "real")) return false;
     if (op->general || !op->t.stream_ok || !op->t.real_ok || op->k1_kernel == 1) return false;
     if (!k1r_fits(op->t.ns_max, op->t.r_n_ovf)) return false;
     return op->k1_kernel == 2 || (long long)S * op->C * K1_STREAM_MIN_IMAGES_DIV >= (long long)op->ctx->sm_count;

@@ -1,4 +1,5 @@
-"""The real-state PnP-ADMM loop (csrc/xupdate_real.cu): from two slices on, for V = eye, the loop carries the
+"""The real-state PnP-ADMM loop (csrc/xupdate_real.cu; opt-in with QMRI_K1_STATE=real - it moves 8 instead of 24
+bytes per pixel-channel but measured no faster than the complex-state kernels, which stay the default): the loop carries the
 sampled-location recurrence c_{k+1} = (y - 2 m_k + m_{k-1} + c_k) / (1 + rho), m_k = A v_k, and only real images cross HBM; the
 complex iterate x_K is materialised after the last iteration.  Checked here against the oracle loop (float64, exact solve) and
 against the complex-state kernels (QMRI_K1_STATE=complex) for every iteration count that takes a different code path
@@ -38,6 +39,7 @@ def test_real_state_loop_general_x0(q, kind, iters, monkeypatch):
     Y[:, 1] *= 2.5                                                    # per-slice dynamic range
     X0 = Fo.adjoint(Y) + 0.3 * smooth_tsmi(70 + iters, S=S, cplx=True)  # not A^H y: the first x-update moves x
     param = {"iter": iters, "gamma": 0.05, "denoiser_type": "single_level"}
+    monkeypatch.setenv("QMRI_K1_STATE", "real")
     monkeypatch.setenv("QMRI_K1R_GROUP", "2")                         # groups of 2 + 1 slices
     x = q.PnP_ADMM(Y, dict(param, F=q.fft_operator(P), net=box_denoiser, X0=X0))
     for s in range(S):
@@ -60,7 +62,9 @@ def test_real_state_loop_builtin_net_graph_and_session_restart(q, monkeypatch):
     sd = unetres.make_state_dict(10, seed=0)
     net = q.UNetRes(sd, in_nc=10)
     param = {"iter": 8, "gamma": 0.05, "X0": X0, "denoiser_type": "single_level", "F": q.fft_operator(P), "net": net}
+    monkeypatch.setenv("QMRI_K1_STATE", "real")
     sess = q.AdmmSession(param, 2)
+    assert sess.xupdate_bytes() == 8
     sess.upload(Y, X0)
     sess.run(8)
     xa = sess.download()
@@ -77,4 +81,9 @@ def test_real_state_loop_builtin_net_graph_and_session_restart(q, monkeypatch):
     assert np.array_equal(xa, xd)
     monkeypatch.setenv("QMRI_K1_STATE", "complex")
     xc = q.PnP_ADMM(Y, param)
-    assert rel_l2(xa, xc) <= 1e-5
+    # two fp32 formulations of the same iteration, 8 passes through a random-init (non-contractive) network: the denoiser
+    # tolerance bounds their distance, as it bounds each one's distance to the oracle
+    assert rel_l2(xa, xc) <= 1e-4
+    xo0 = pnp_admm(Y[:, 0], {"iter": 8, "gamma": 0.05, "F": Fo, "X0": X0[..., 0],
+                             "net": lambda v: unetres.denoise_matlab_layout(sd, v)}, solver="exact")
+    assert rel_l2(xc[..., 0], xo0) <= 1e-4 and rel_l2(xa[..., 0], xo0) <= 1e-4
