@@ -14,7 +14,8 @@
 // Kernel: persistent, warp-specialised.  Work item = (tile of 128 pixels, atom range).  Warp 0 (TMA): the pixel tile (real and
 // imaginary K-major rows, 2 x 16 KB, loaded once per work item) and a ring of 128-atom tiles (16 KB each) into 128B-swizzled
 // shared memory.  Warp 1 (MMA): per atom tile 2 x 4 tcgen05.mma (M128 x N128 x K8) into one of two TMEM accumulator pairs.
-// Warps 2-9 (epilogue; two per TMEM lane quarter, each taking 64 of the tile's 128 atom columns): thread = pixel; tcgen05.ld of
+// Warps 2-5 (epilogue; QMRI_K2_EPI_WARPS=8: warps 2-9, two per TMEM lane quarter, each taking 64 of the tile's 128 atom
+// columns - measured no faster): thread = pixel; tcgen05.ld of
 // the real and imaginary accumulators (issued one 32-column chunk ahead of the arithmetic), s = re^2 + im^2, the maximum of each
 // 16-atom group as a depth-4 tree (3 FP32 instructions per score; with one or two warps per scheduler a 16-long dependent
 // FMNMX chain was the limiter: ncu showed the epilogue warps issuing 41 % of the cycles).  The thread keeps the TWO BEST GROUPS
@@ -29,6 +30,7 @@
 // (relative) of the FP32 scores, so an atom can be missed only inside a reference near-tie (top-2 gap < 1e-6).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -43,8 +45,7 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int MT_EPI_WARPS = 8;               // two warps per TMEM lane quarter: each takes 64 of a tile's 128 atom columns
-constexpr int MT_THREADS = 64 + 32 * MT_EPI_WARPS;
+constexpr int MT_THREADS_MAX = 64 + 32 * 8;    // TMA warp + MMA warp + 4 or 8 epilogue warps (EW)
 constexpr int MT_BM = 128;                  // pixels per tile
 constexpr int MT_BN = 128;                  // atoms per tile
 constexpr int MT_KF = 32;                   // floats per operand row (128 B = one swizzle row)
@@ -92,8 +93,8 @@ __global__ void match_prep_kernel(const float* __restrict__ x_re, const float* _
     for (int j = 0; j < MT_KF / 4; ++j) row[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-template <int C, bool CPLX>
-__global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+template <int C, bool CPLX, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                 const MtParams p) {
     extern __shared__ unsigned char mt_smem_raw[];
     const uint32_t raw = smem_u32(mt_smem_raw);
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
         mbar_init(a_empty, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], MT_EPI_WARPS);
+            mbar_init(&tempty[a], EW);
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
@@ -204,7 +205,8 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
     } else {
         // ================= epilogue warps: thread = (pixel = TMEM lane, half of the tile's atom columns) =================
         const int lg = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;        // columns [64 half, 64 half + 64) of every accumulator
+        constexpr int NCH = 4 / (EW / 4);        // 32-column chunks of a tile per warp: 4 (EW = 4) or 2 (EW = 8, two warps per lane quarter)
+        const int half = EW == 8 ? (warp - 2) >> 2 : 0;  // EW = 8: columns [64 half, 64 half + 64) of every accumulator
         const int row = lg * 32 + lane;
         int it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
             // Accumulator reads run one 32-column chunk ahead of the arithmetic: a chunk's tcgen05.ld is issued before the previous
             // chunk is scored and waited for afterwards (tcgen05.wait::ld covers every outstanding load of the thread).
             uint32_t reA[32], imA[32], reB[32], imB[32];
-            auto tile_addr = [&](int i) { return tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((i & 1) * 2 * MT_BN + 64 * half); };
+            auto tile_addr = [&](int i) { return tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((i & 1) * 2 * MT_BN + 32 * NCH * half); };
             if (t0 < t1) {
                 mbar_wait(&tfull[it & 1], (it >> 1) & 1);
                 tc_fence_after();
@@ -262,9 +264,17 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
             }
             for (int t = t0; t < t1; ++t, ++it) {
                 const int ab = it & 1;
-                const int gid = (t - t0) * (MT_BN / 16) + 4 * half;
-                load_chunk(tile_addr(it) + 32, reB, imB);
-                score_chunk(reA, imA, gid);
+                const int gid = (t - t0) * (MT_BN / 16) + 2 * NCH * half;
+                if (NCH == 4) {
+                    load_chunk(tile_addr(it) + 32, reB, imB);
+                    score_chunk(reA, imA, gid);
+                    tc_wait_ld();
+                    load_chunk(tile_addr(it) + 64, reA, imA);
+                    score_chunk(reB, imB, gid + 2);
+                    tc_wait_ld();
+                }
+                load_chunk(tile_addr(it) + 32 * (NCH - 1), reB, imB);
+                score_chunk(reA, imA, gid + 2 * (NCH - 2));
                 tc_wait_ld();
                 // this warp's share of the tile is in registers: hand the buffer back
                 tc_fence_before();
@@ -275,7 +285,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(const __grid_co
                     tc_fence_after();
                     load_chunk(tile_addr(it + 1), reA, imA);
                 }
-                score_chunk(reB, imB, gid + 2);
+                score_chunk(reB, imB, gid + 2 * (NCH - 1));
                 if (t + 1 < t1) tc_wait_ld();
             }
             // rescore the 2 x 16 candidates with the FMA kernel's exact expression on the original fp32 data
@@ -384,17 +394,25 @@ int launch_c(qmri_ctx* ctx, const K2TcDict& d, const K2Params& p, float* A, int6
     }
     m.nsplit = nsplit;
     const int grid = (int)std::min<int64_t>((int64_t)m.ptiles * nsplit, ctx->sm_count);
-    static bool configured_dev[QMRI_MAX_DEV][2] = {};
-    bool& conf = configured_dev[qmri_dev_slot(ctx)][p.x_im ? 1 : 0];
+    static const int ew_env = getenv("QMRI_K2_EPI_WARPS") ? atoi(getenv("QMRI_K2_EPI_WARPS")) : 0;  // tuning knob: 4 or 8
+    const int ew = ew_env == 8 ? 8 : 4;
+    static bool configured_dev[QMRI_MAX_DEV][4] = {};
+    bool& conf = configured_dev[qmri_dev_slot(ctx)][(p.x_im ? 1 : 0) + (ew == 8 ? 2 : 0)];
+    const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(d.mapB);
+#define MT_LAUNCH(CPLX, EW)                                                                                                      \
+    do {                                                                                                                          \
+        if (!conf) QCUDA(cudaFuncSetAttribute(match_tc_kernel<C, CPLX, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM)); \
+        conf = true;                                                                                                              \
+        match_tc_kernel<C, CPLX, EW><<<grid, 64 + 32 * EW, MT_SMEM, ctx->stream>>>(tmA, tmB, m);                                  \
+    } while (0)
     if (p.x_im) {
-        if (!conf) QCUDA(cudaFuncSetAttribute(match_tc_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
-        conf = true;
-        match_tc_kernel<C, true><<<grid, MT_THREADS, MT_SMEM, ctx->stream>>>(tmA, *reinterpret_cast<const CUtensorMap*>(d.mapB), m);
+        if (ew == 8) MT_LAUNCH(true, 8);
+        else MT_LAUNCH(true, 4);
     } else {
-        if (!conf) QCUDA(cudaFuncSetAttribute(match_tc_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
-        conf = true;
-        match_tc_kernel<C, false><<<grid, MT_THREADS, MT_SMEM, ctx->stream>>>(tmA, *reinterpret_cast<const CUtensorMap*>(d.mapB), m);
+        if (ew == 8) MT_LAUNCH(false, 8);
+        else MT_LAUNCH(false, 4);
     }
+#undef MT_LAUNCH
     QLAUNCH_CHECK(ctx);
     return QMRI_OK;
 }

@@ -808,7 +808,7 @@ struct qmri_admm {
     // real-state loop (xupdate_real.cu): c_k and m_{k-1} on the sampled locations, and a second v buffer so that the last
     // x-update still finds v_{K-2}
     bool lean = false;
-    int lean_group = 0;       // slices per forward / solve / adjoint triple (sized so that v is re-read from L2)
+    int lean_group = 0;       // slices per forward / solve / adjoint triple (QMRI_K1R_GROUP; default: all)
     DevBuf v_alt, cstate, mprev;
     float *h_in = nullptr, *h_out = nullptr;  // pinned, host-callback path
     bool uploaded = false;
@@ -853,7 +853,7 @@ extern "C" int qmri_admm_create(qmri_op* op, int S, const qmri_admm_params* para
                 st->lean ? "real" : "complex", (int)op->general, (int)op->t.stream_ok, (int)op->t.real_ok, op->t.ns_max, op->t.r_n_ovf);
     if (st->lean) {
         const char* env = getenv("QMRI_K1R_GROUP");  // tuning knob: slices per kernel triple
-        st->lean_group = std::max(1, std::min(S, env ? atoi(env) : 24));
+        st->lean_group = std::max(1, std::min(S, env ? atoi(env) : S));  // one launch triple measured fastest (L2-sized groups: +33 %)
         const size_t ns = (size_t)op->t.ns_max;
         r |= st->v_alt.ensure(n * 4);
         r |= st->cstate.ensure(k1r_state_elems(S, op->C, (int)ns) * sizeof(float2));
@@ -962,10 +962,11 @@ static int admm_k1(qmri_admm* st, bool write_x) {
 
 // ---- real-state loop (xupdate_real.cu) ---------------------------------------------------------------------------------
 // Opt-in (QMRI_K1_STATE=real) where the streaming kernels would run anyway (two slices or more), V is the identity and the mask
-// fits the folded work-item tables.  Measured on B200 at 120 slices (profiles/r02_k1_real_vs_complex.md): the real kernels move
-// 8 instead of 24 bytes per pixel-channel and run half the FFT work, yet take the same time (forward 39 vs 42 us, adjoint 58 vs
-// 58 us per 24 slices) - both families are bound by the critical path of the sparse m-direction sums between two CTA barriers,
-// not by bytes or FFT flops - so the complex-state kernels stay the default and the roofline is reported against their 20 B.
+// fits the folded work-item tables.  Measured on B200 at 120 slices (profiles/r02_k1_real_vs_complex.md): the real kernels move 8
+// (12 with the second read of v) instead of 24 bytes per pixel-channel and run half the FFT work, and take 3.20 instead of 4.13 us
+// per slice-iteration - both families are bound by the sparse m-direction sums between two CTA barriers, not by bytes or FFT
+// flops.  Counted against the 8 bytes it moves that is 0.19 of the HBM roofline (0.34 - 0.38 for the complex-state kernels at their
+// 20), and the x-update is 0.6 % of the job: the complex-state kernels stay the default.
 static bool admm_lean_eligible(const qmri_op* op, int S) {
     const char* env = getenv("QMRI_K1_STATE");
     if (!env || strcmp(env, "real")) return false;

@@ -233,6 +233,8 @@ int unetres_reserve(qmri_net* net, int S, int H, int W) {
     for (int l = 0; l < 4; ++l) per_slice += 3 * level_elems(l, H, W);
     // chunk the slice batch so the workspace stays modest and activations stay L2-friendly
     // balanced chunks: 120 slices run as 8 x 15, not 7 x 16 + 8 (a half-empty last chunk fills the machine worse)
+    const char* env_chunk = getenv("QMRI_NET_CHUNK");  // tuning knob: most slices per pass (default unetres.h max_chunk)
+    if (env_chunk && atoi(env_chunk) > 0) net->max_chunk = atoi(env_chunk);
     const int nchunks = (S + net->max_chunk - 1) / net->max_chunk;
     int chunk = nchunks > 0 ? (S + nchunks - 1) / nchunks : S;
     size_t need = per_slice * chunk;
