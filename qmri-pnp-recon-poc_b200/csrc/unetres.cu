@@ -231,8 +231,8 @@ static size_t level_elems(int lvl, int H, int W) { return (size_t)(H >> lvl) * (
 int unetres_reserve(qmri_net* net, int S, int H, int W) {
     size_t per_slice = 0;
     for (int l = 0; l < 4; ++l) per_slice += 3 * level_elems(l, H, W);
-    // chunk the slice batch so the workspace stays modest and activations stay L2-friendly
-    // balanced chunks: 120 slices run as 8 x 15, not 7 x 16 + 8 (a half-empty last chunk fills the machine worse)
+    // chunk very large slice batches so that the workspace stays bounded (9 GB at 128 slices); balanced chunks: 200 slices run as
+    // 2 x 100, not 128 + 72
     const char* env_chunk = getenv("QMRI_NET_CHUNK");  // tuning knob: most slices per pass (default unetres.h max_chunk)
     if (env_chunk && atoi(env_chunk) > 0) net->max_chunk = atoi(env_chunk);
     const int nchunks = (S + net->max_chunk - 1) / net->max_chunk;

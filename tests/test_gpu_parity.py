@@ -283,6 +283,24 @@ def test_denoiser_matlab_layout_and_wrapper(q, nets):
     assert q.denoiseImage_PnP_ADMM(A, net, "yes", False) is None  # the reference's soft failure
 
 
+def test_denoiser_chunked_passes_equal_single_pass(q, monkeypatch):
+    """Slice batches beyond unetres.h's max_chunk run as balanced passes (QMRI_NET_CHUNK lowers the limit): 5 slices as 2 + 2 + 1
+    against one pass of 5."""
+    from oracle import unetres
+    sd = unetres.make_state_dict(10, seed=0)
+    rng = np.random.default_rng(5)
+    A = rng.random((224, 224, 10, 5))
+    one = q.UNetRes(sd, in_nc=10)
+    y1 = one.denoise(A)
+    monkeypatch.setenv("QMRI_NET_CHUNK", "2")
+    three = q.UNetRes(sd, in_nc=10)
+    y3 = three.denoise(A)
+    assert y1.shape == y3.shape == (224, 224, 10, 5)
+    assert rel_l2(y3, y1) <= 1e-5            # tile shapes / split-K follow the pass size: not bitwise
+    ref = unetres.denoise_matlab_layout(sd, A[..., 4])
+    assert rel_l2(y3[..., 4], ref) <= TOL_DENOISER
+
+
 def test_denoiser_multi_level_11_channels(q):
     import torch
     from oracle import unetres
@@ -706,7 +724,7 @@ def test_full_size_120_slices_recon_and_matching(q, ops):
         assert rel_l2(x[..., s], xs) <= TOL_DENOISER                   # tile / split-K / x-update kernel choices depend on the batch size: not bitwise
     perm = rng.permutation(S)                                          # (b)
     xp = q.PnP_ADMM(np.ascontiguousarray(Y[:, perm]), dict(param, X0=np.ascontiguousarray(X0[..., perm])))
-    assert rel_l2(xp, x[..., perm]) <= TOL_DENOISER       # the last denoiser chunk (120 = 7 x 16 + 8) picks other tile shapes: not bitwise
+    assert rel_l2(xp, x[..., perm]) <= TOL_DENOISER       # slices sit at other positions of the denoiser pass (tile shapes / split-K follow the position): not bitwise
     assert np.isfinite(xp).all()
     from oracle.sampling import FOperator                              # (c)
     Fo = FOperator(Po)
