@@ -212,8 +212,9 @@ int qmri_match(qmri_dict* d, const void* x, int x_dtype, int64_t npix, float* qm
 int qmri_match_dev(qmri_dict* d, const float* x_re, const float* x_im, int64_t npix, float* qmap_dev, float* pd_dev,
                    float* mt_dev, int32_t* dm_dev);
 /* Atom-sharded matching (BASELINE config 5): local packed keys
- *   key = float_bits(score^2) << 32 | (0xFFFFFFFF - global_atom_index)
- * (max over ranks of the key = max score, lowest index on ties = MATLAB's first-index rule),
+ *   key = float_bits(|<d, x s>|^2) << 32 | (0xFFFFFFFF - global_atom_index)
+ * (max over ranks of the key = max score, lowest index on ties = MATLAB's first-index rule; s = a power of two that depends on
+ * the pixel's data alone and keeps the squared score inside the fp32 range - the same on every rank, atom range and kernel),
  * reduced by the caller (NCCL max over uint64 / int64), then finished from the reduced keys. */
 int qmri_match_keys_dev(qmri_dict* d, const float* x_re, const float* x_im, int64_t npix, uint64_t* keys_dev);
 int qmri_match_finish_dev(qmri_dict* d, const float* x_re, const float* x_im, int64_t npix, const uint64_t* keys_dev,

@@ -51,6 +51,21 @@ __global__ void __launch_bounds__(K2_THREADS) match_kernel(K2Params p) {
             if (CPLX) xi[i][c] = (ok && c < p.C) ? __ldg(p.x_im + (int64_t)c * p.npix + pix) : 0.f;
         }
     }
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {  // per-pixel power-of-two scale (match_score.cuh): keeps |<d, x>|^2 inside the fp32 range
+        float m = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            m = fmaxf(m, fabsf(xr[i][c]));
+            if (CPLX) m = fmaxf(m, fabsf(xi[i][c]));
+        }
+        const float sc = k2_pixel_scale(m);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            xr[i][c] *= sc;
+            if (CPLX) xi[i][c] *= sc;
+        }
+    }
     float best[PX];
     int bgrp[PX];  // winning group, counted from ka in units of K2_GROUP atoms
 #pragma unroll
@@ -156,7 +171,7 @@ __global__ void match_finish_kernel(K2Finish p) {
         p.pd[2 * pix] = sr / nd;
         p.pd[2 * pix + 1] = -si / nd;
     }
-    if (p.mt) p.mt[pix] = sqrtf(fmaf(si, si, sr * sr));
+    if (p.mt) p.mt[pix] = hypotf(sr, si);  // no intermediate square: |ip| keeps the whole fp32 range, like abs(ip) in the reference
     if (p.dm) p.dm[pix] = (int32_t)idx + 1;
     if (p.qmap)
         for (int q = 0; q < p.Q; ++q) {

@@ -81,8 +81,14 @@ __global__ void match_prep_kernel(const float* __restrict__ x_re, const float* _
 #pragma unroll
     for (int j = 0; j < MT_KF; ++j) v[j] = 0.f;
     if (pix < npix && x) {
+        float m = 0.f;  // per-pixel power-of-two scale over both parts (match_score.cuh)
         for (int c = 0; c < C; ++c) {
-            const float a = __ldg(x + (int64_t)c * npix + pix);
+            m = fmaxf(m, fabsf(__ldg(x_re + (int64_t)c * npix + pix)));
+            if (x_im) m = fmaxf(m, fabsf(__ldg(x_im + (int64_t)c * npix + pix)));
+        }
+        const float sc = k2_pixel_scale(m);
+        for (int c = 0; c < C; ++c) {
+            const float a = sc * __ldg(x + (int64_t)c * npix + pix);
             const float hi = to_tf32(a);
             v[c] = hi;
             v[C + c] = to_tf32(a - hi);
@@ -292,10 +298,21 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) match_tc_kernel(const __grid_
             const int64_t pix = (int64_t)pt * MT_BM + row;
             if (pix < p.npix && g1k >= 0) {
                 float xr[C], xi[CPLX ? C : 1];
+                float m = 0.f;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     xr[c] = __ldg(p.x_re + (int64_t)c * p.npix + pix);
-                    if (CPLX) xi[c] = __ldg(p.x_im + (int64_t)c * p.npix + pix);
+                    m = fmaxf(m, fabsf(xr[c]));
+                    if (CPLX) {
+                        xi[c] = __ldg(p.x_im + (int64_t)c * p.npix + pix);
+                        m = fmaxf(m, fabsf(xi[c]));
+                    }
+                }
+                const float psc = k2_pixel_scale(m);  // the same per-pixel scale as the operand pre-pass and the FMA kernel
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    xr[c] *= psc;
+                    if (CPLX) xi[c] *= psc;
                 }
                 float best = -1.f;
                 int64_t win = -1;

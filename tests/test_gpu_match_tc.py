@@ -118,3 +118,22 @@ def test_tensor_pipe_ties_nan_zero_and_ranges(q, monkeypatch):
     for h in parts:
         h.close()
     whole.close()
+
+
+@pytest.mark.parametrize("pipe", ["tensor", "fma"])
+def test_matching_is_invariant_to_the_pixel_amplitude(q, monkeypatch, pipe):
+    """The reference ranks atoms by abs(ip); the kernels rank by |ip|^2, which halves the fp32 exponent range.  A per-pixel power-of-two
+    scale (csrc/match_score.cuh) keeps the squared scores in range: signatures of amplitude 1e-30 ... 1e+25 match the same atoms as
+    at amplitude 1, and mt / pd follow the original amplitude."""
+    import benchdata
+    monkeypatch.setenv("QMRI_K2_PIPE", pipe)
+    d = benchdata.make_dictionary(K_target=4000, cut=3, seed=4)
+    X = _pixels(d, 600, True, seed=9)
+    par = {"f": {"qout": 1, "pdout": 1, "dmout": 1, "mtout": 1}}
+    ref = q.mrf_dtm_cpu(d, {"X": X}, par)
+    for amp in (1e-30, 1e-22, 3e-12, 7e11, 1e25):
+        out = q.mrf_dtm_cpu(d, {"X": X * amp}, par)
+        assert np.array_equal(out["dm"], ref["dm"]), (pipe, amp)
+        assert np.array_equal(out["qmap"], ref["qmap"])
+        assert rel_l2(out["mt"].astype(np.float64), ref["mt"].astype(np.float64) * amp) < 1e-5
+        assert rel_l2(out["pd"].astype(np.complex128), ref["pd"].astype(np.complex128) * amp) < 1e-5
