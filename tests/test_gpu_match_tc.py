@@ -123,7 +123,7 @@ def test_tensor_pipe_ties_nan_zero_and_ranges(q, monkeypatch):
 @pytest.mark.parametrize("pipe", ["tensor", "fma"])
 def test_matching_is_invariant_to_the_pixel_amplitude(q, monkeypatch, pipe):
     """The reference ranks atoms by abs(ip); the kernels rank by |ip|^2, which halves the fp32 exponent range.  A per-pixel power-of-two
-    scale (csrc/match_score.cuh) keeps the squared scores in range: signatures of amplitude 1e-30 ... 1e+25 match the same atoms as
+    scale (csrc/match_score.cuh) keeps the squared scores in range: signatures of amplitude 2^-100 ... 2^83 match the same atoms as
     at amplitude 1, and mt / pd follow the original amplitude."""
     import benchdata
     monkeypatch.setenv("QMRI_K2_PIPE", pipe)
@@ -131,7 +131,7 @@ def test_matching_is_invariant_to_the_pixel_amplitude(q, monkeypatch, pipe):
     X = _pixels(d, 600, True, seed=9)
     par = {"f": {"qout": 1, "pdout": 1, "dmout": 1, "mtout": 1}}
     ref = q.mrf_dtm_cpu(d, {"X": X}, par)
-    for amp in (1e-30, 1e-22, 3e-12, 7e11, 1e25):
+    for amp in (2.0 ** -100, 2.0 ** -75, 2.0 ** -40, 2.0 ** 40, 2.0 ** 83):   # powers of two: the fp32 signatures are exact multiples
         out = q.mrf_dtm_cpu(d, {"X": X * amp}, par)
         assert np.array_equal(out["dm"], ref["dm"]), (pipe, amp)
         assert np.array_equal(out["qmap"], ref["qmap"])
