@@ -51,6 +51,7 @@
 namespace {
 
 constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int PAIR_THREADS = 224;  // the CTA-pair kernel adds warp 6: a second MMA issuer (see tc_conv3x3_pair_kernel)
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;        // one 128-byte swizzle row of bf16
 constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB
@@ -181,6 +182,8 @@ struct TcK {
     int BW, BH, tiles_x, tiles_y;
     int relu, nsplit;
     int cluster_splitk;  // split-K partials meet in the shared memory of a thread-block cluster of nsplit CTAs (one work item per CTA)
+    int dual;            // CTA-pair kernel, Cout = 64: a second warp issues the a_lo w_hi MMAs into their own accumulator columns
+    int resw;            // CTA-pair kernel, Cin = Cout = 64: the layer's weights stay resident in shared memory
 };
 
 #define TC_TRACE(slot, val)                                                   \
@@ -642,7 +645,8 @@ struct PairCfg {
     static constexpr uint32_t B_STAGE = B1_BYTES + B2_BYTES;
     static constexpr int AS = (NA == 128) ? 3 : 2;
     static constexpr int BS = (NA == 128) ? 8 : (STACK ? 5 : 4);
-    static constexpr uint32_t TMEM_COLS = 2 * NA;                // two accumulators
+    static constexpr bool DUAL_OK = STACK && NA == 128;          // room in TMEM for a separate accumulator of the a_lo w_hi product
+    static constexpr uint32_t TMEM_COLS = DUAL_OK ? 512 : 2 * NA; // two accumulators (+ 2 x NA/2 columns for the second issuer's)
     static constexpr size_t SMEM = (size_t)AS * A_SLOT + (size_t)BS * B_STAGE + 1024 + 256;
 };
 
@@ -682,15 +686,23 @@ __device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t desc_a, uint64
 
 // 16 consecutive output channels of this thread's pixel from the accumulator (STACK: sum of the two column blocks)
 template <int NA, int STACK>
-__device__ __forceinline__ void pair_acc16(uint32_t taddr, int c0, float* v) {
+__device__ __forceinline__ void pair_acc16(uint32_t taddr, uint32_t taddr2, int c0, float* v) {
     uint32_t a[16];
     tc_ld16(taddr + c0, a);
     if (STACK) {
         uint32_t b[16];
         tc_ld16(taddr + NA / 2 + c0, b);
-        tc_wait_ld();
+        if (taddr2) {  // dual-issuer mode: a_lo w_hi was accumulated in its own columns
+            uint32_t c[16];
+            tc_ld16(taddr2 + c0, c);
+            tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+            for (int j = 0; j < 16; ++j) v[j] = (__uint_as_float(a[j]) + __uint_as_float(c[j])) + __uint_as_float(b[j]);
+        } else {
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+        }
     } else {
         tc_wait_ld();
 #pragma unroll
@@ -699,7 +711,7 @@ __device__ __forceinline__ void pair_acc16(uint32_t taddr, int c0, float* v) {
 }
 
 template <int NA, int STACK>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
 tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                        const __grid_constant__ CUtensorMap tmB_h2, const TcK p) {
@@ -730,18 +742,31 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const int cidx = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const uint32_t slab_bytes = (uint32_t)((p.BH + 2) * p.BW * 128);
     const uint32_t dy_bytes = (uint32_t)(p.BW * 128);
+    // Dual-issuer mode (Cout = 64 layers).  One thread issues a tcgen05.mma every ~103 cycles at best, whatever its N
+    // (profiles/r02_tmem_a_bench.txt), so the two MMAs of a K step - N = 128 and N = 64, 96 cycles of tensor time - took ~206.  Warp 1
+    // keeps a_hi x [w_hi | w_lo]; warp 6 issues a_lo x w_hi into its OWN accumulator columns (MMAs of different threads are not ordered
+    // against each other, so they must not share an accumulator); the epilogue adds the third block.
+    const bool dual = Cfg::DUAL_OK && p.dual;
+    // Resident-weight mode (Cin = Cout = 64 layers).  With Cout = 64 a 128-pixel tile re-streamed the whole layer's weights (108 KB per
+    // CTA: nine taps of [w_hi ; w_lo] and w_hi) next to 120 KB of activation slabs - 66 B/clk per SM at the tensor rate against the
+    // ~43 B/clk an SM gets from L2 through TMA.  Here the nine weight tiles are loaded ONCE per CTA into the space of the weight ring and
+    // the third slab stage; the main loop streams activation slabs only (two stages).
+    const bool resw = Cfg::DUAL_OK && p.resw && p.Cin == TC_BK;
+    const int AS_EFF = resw ? 2 : AS;
+    unsigned char* smemW = smem + (size_t)2 * Cfg::A_SLOT;   // resw: nine B_STAGE-sized weight tiles, tap-major
 
     if (threadIdx.x == 0) {
+        const uint32_t nissue = dual ? 2u : 1u;  // MMA issuers that commit on the stage / accumulator barriers
         for (int s = 0; s < AS; ++s) {
             mbar_init(&fullA[s], 1);
-            mbar_init(&emptyA[s], 1);
+            mbar_init(&emptyA[s], nissue);
         }
         for (int s = 0; s < BS; ++s) {
             mbar_init(&fullB[s], 1);
-            mbar_init(&emptyB[s], 1);
+            mbar_init(&emptyB[s], nissue);
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull[a], 1);
+            mbar_init(&tfull[a], nissue);
             mbar_init(&tempty[a], 8);  // 4 epilogue warps of each CTA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -770,6 +795,15 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         if (lane == 0) {
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
+            if (resw && cidx < total_work) {  // the layer's weights, once: completion on the leader's fullB[0]
+                if (crank == 0) mbar_expect_tx(&fullB[0], 2 * 9 * Cfg::B_STAGE);
+                const uint32_t barW = mapa_rank(smem_u32(&fullB[0]), 0);
+                for (int tap = 0; tap < 9; ++tap) {
+                    unsigned char* wp = smemW + (size_t)tap * Cfg::B_STAGE;
+                    tma2_load_2d(wp, crank == 0 ? &tmB_hi : &tmB_lo, barW, tap * p.Cin, 0);
+                    tma2_load_2d(wp + Cfg::B1_BYTES, &tmB_h2, barW, tap * p.Cin, crank * (NOUT / 2));
+                }
+            }
             for (int w = cidx; w < total_work; w += nclusters) {
                 const int split = w % p.nsplit;
                 const int r = w / p.nsplit;
@@ -789,11 +823,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     const uint32_t barA = mapa_rank(smem_u32(&fullA[sa]), 0);
                     tma2_load_4d(st, &tmA_hi, barA, cb * TC_BK, x0 + dxi - 1, y0 - 1, s);
                     tma2_load_4d(st + Cfg::A_PLANE, &tmA_lo, barA, cb * TC_BK, x0 + dxi - 1, y0 - 1, s);
-                    if (++sa == AS) {
+                    if (++sa == AS_EFF) {
                         sa = 0;
                         pa ^= 1;
                     }
-                    for (int dyi = 0; dyi < 3; ++dyi) {
+                    for (int dyi = 0; dyi < 3 && !resw; ++dyi) {
                         const int kcol = (dyi * 3 + dxi) * p.Cin + cb * TC_BK;
                         TC_TRACE(0, (w << 12) | (u << 4) | (2 + dyi));
                         mbar_wait(&emptyB[sb], pb ^ 1);
@@ -826,6 +860,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             int it = 0;
+            if (resw && cidx < total_work) {
+                mbar_wait(&fullB[0], 0);  // the resident weights have landed in both CTAs
+                tc_fence_after();
+            }
             for (int w = cidx; w < total_work; w += nclusters, ++it) {
                 const int split = w % p.nsplit;
                 const int u0 = (split * U) / p.nsplit, u1 = ((split + 1) * U) / p.nsplit;
@@ -842,9 +880,12 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     const uint32_t ha = smem_u32(smem + (size_t)sa * Cfg::A_SLOT);
                     for (int dyi = 0; dyi < 3; ++dyi) {
                         TC_TRACE(1, (w << 12) | (u << 4) | (2 + dyi));
-                        mbar_wait(&fullB[sb], pb);
-                        tc_fence_after();
-                        const uint32_t sbase = smem_u32(smemB + (size_t)sb * Cfg::B_STAGE);
+                        if (!resw) {
+                            mbar_wait(&fullB[sb], pb);
+                            tc_fence_after();
+                        }
+                        const uint32_t sbase = resw ? smem_u32(smemW + (size_t)(dyi * 3 + (u - 3 * (u / 3))) * Cfg::B_STAGE)
+                                                    : smem_u32(smemB + (size_t)sb * Cfg::B_STAGE);
                         const uint64_t a_hi = umma_desc(ha + dyi * dy_bytes), a_lo = umma_desc(ha + Cfg::A_PLANE + dyi * dy_bytes);
                         const uint64_t b_1 = umma_desc(sbase), b_2 = umma_desc(sbase + Cfg::B1_BYTES);
 #pragma unroll
@@ -853,26 +894,82 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             const uint32_t acc = ((u - u0) | dyi | k) ? 1u : 0u;
                             if (STACK) {
                                 tc2_mma(tmem_d, a_hi + ko, b_1 + ko, idesc_full, acc);   // [a_hi w_hi | a_hi w_lo]
-                                tc2_mma(tmem_d, a_lo + ko, b_2 + ko, idesc_half, 1u);    // += a_lo w_hi into the first block
+                                if (!dual) tc2_mma(tmem_d, a_lo + ko, b_2 + ko, idesc_half, 1u);    // += a_lo w_hi into the first block
                             } else {
                                 tc2_mma(tmem_d, a_hi + ko, b_1 + ko, idesc_full, acc);
                                 tc2_mma(tmem_d, a_hi + ko, b_2 + ko, idesc_full, 1u);
                                 tc2_mma(tmem_d, a_lo + ko, b_1 + ko, idesc_full, 1u);
                             }
                         }
-                        tc2_commit(&emptyB[sb]);  // frees the stage in both CTAs
-                        if (++sb == BS) {
-                            sb = 0;
-                            pb ^= 1;
+                        if (!resw) {
+                            tc2_commit(&emptyB[sb]);  // frees the stage in both CTAs
+                            if (++sb == BS) {
+                                sb = 0;
+                                pb ^= 1;
+                            }
                         }
                     }
                     tc2_commit(&emptyA[sa]);
-                    if (++sa == AS) {
+                    if (++sa == AS_EFF) {
                         sa = 0;
                         pa ^= 1;
                     }
                 }
                 tc2_commit(&tfull[ab]);  // accumulator complete: wakes the epilogue warps of both CTAs
+            }
+        }
+    } else if (warp == 6) {
+        // ================= second MMA issuer (leader CTA only, dual-issuer mode): a_lo x w_hi into its own accumulator =================
+        if (lane == 0 && crank == 0 && dual) {
+            const uint32_t idesc_half = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24) | ((uint32_t)((NA / 2) >> 3) << 17);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int w = cidx; w < total_work; w += nclusters, ++it) {
+                const int split = w % p.nsplit;
+                const int u0 = (split * U) / p.nsplit, u1 = ((split + 1) * U) / p.nsplit;
+                const int ab = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                if (resw && it == 0) {
+                    mbar_wait(&fullB[0], 0);
+                    tc_fence_after();
+                }
+                mbar_wait(&tempty[ab], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d2 = tmem_base + (uint32_t)(2 * NA + ab * (NA / 2));
+                for (int u = u0; u < u1; ++u) {
+                    mbar_wait(&fullA[sa], pa);
+                    tc_fence_after();
+                    const uint32_t ha = smem_u32(smem + (size_t)sa * Cfg::A_SLOT);
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        if (!resw) {
+                            mbar_wait(&fullB[sb], pb);
+                            tc_fence_after();
+                        }
+                        const uint32_t sbase = resw ? smem_u32(smemW + (size_t)(dyi * 3 + (u - 3 * (u / 3))) * Cfg::B_STAGE)
+                                                    : smem_u32(smemB + (size_t)sb * Cfg::B_STAGE);
+                        const uint64_t a_lo = umma_desc(ha + Cfg::A_PLANE + dyi * dy_bytes);
+                        const uint64_t b_2 = umma_desc(sbase + Cfg::B1_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            tc2_mma(tmem_d2, a_lo + ko, b_2 + ko, idesc_half, ((u - u0) | dyi | k) ? 1u : 0u);
+                        }
+                        if (!resw) {
+                            tc2_commit(&emptyB[sb]);
+                            if (++sb == BS) {
+                                sb = 0;
+                                pb ^= 1;
+                            }
+                        }
+                    }
+                    tc2_commit(&emptyA[sa]);
+                    if (++sa == AS_EFF) {
+                        sa = 0;
+                        pa ^= 1;
+                    }
+                }
+                tc2_commit(&tfull[ab]);
             }
         }
     } else {
@@ -895,6 +992,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             const bool ok = live && (x < p.W) && (y < p.H);
             const size_t o = (((size_t)s * p.H + y) * p.W + x) * p.Cout + (size_t)nt * NOUT;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * NA);
+            const uint32_t taddr2 = dual ? tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(2 * NA + ab * (NA / 2)) : 0u;
             const uint32_t tempty_leader = mapa_rank(smem_u32(&tempty[ab]), 0);
             if (lane == 0) TC_TRACE(2 + lg, (w << 12) | 1);
             if (p.nsplit == 1) {
@@ -923,7 +1021,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     for (int c1 = 0; c1 < PRE; c1 += 16) {
                         const int cc = h0 + c1;
                         float v[16];
-                        pair_acc16<NA, STACK>(taddr, cc, v);
+                        pair_acc16<NA, STACK>(taddr, taddr2, cc, v);
                         if (has_r1) {
                             add_split8(v, rh[c1 / 8], rl[c1 / 8]);
                             add_split8(v + 8, rh[c1 / 8 + 1], rl[c1 / 8 + 1]);
@@ -950,7 +1048,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
 #pragma unroll 1
                     for (int cc = 0; cc < NOUT; cc += 16) {
                         float v[16];
-                        pair_acc16<NA, STACK>(taddr, cc, v);
+                        pair_acc16<NA, STACK>(taddr, taddr2, cc, v);
                         float4* d = reinterpret_cast<float4*>(prow + cc);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -1194,6 +1292,8 @@ int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
     k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
     k.relu = p.relu; k.nsplit = nsplit; k.trace = nullptr;
     k.cluster_splitk = cluster_splitk;
+    k.dual = 0;
+    k.resw = 0;
     if (BN == 64) {
         if (p.mode == TC_CONV3X3) return launch_tc<64, 0>(ctx, maps, k, grid);
         if (p.mode == TC_DOWN2X2) return launch_tc<64, 1>(ctx, maps, k, grid);
@@ -1260,8 +1360,14 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
     const int work = groups * nsplit;
     const int nclusters = work < max_clusters ? work : max_clusters;
     cudaLaunchConfig_t cfg = {};
+    // A/B switches (tests, profiling): QMRI_TC_DUAL=1 turns the second MMA issuer on (measured 3 % slower: off by default),
+    // QMRI_TC_RESW=0 turns the resident weights of the 64 -> 64 layers off
+    static const bool dual_on = getenv("QMRI_TC_DUAL") && !strcmp(getenv("QMRI_TC_DUAL"), "1");
+    static const bool resw_off = getenv("QMRI_TC_RESW") && !strcmp(getenv("QMRI_TC_RESW"), "0");
+    k.dual = (Cfg::DUAL_OK && dual_on) ? 1 : 0;
+    k.resw = (Cfg::DUAL_OK && !resw_off && p.Cin == TC_BK) ? 1 : 0;
     cfg.gridDim = dim3(nclusters * 2);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(PAIR_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[2];
@@ -1319,7 +1425,7 @@ int conv3x3_tc_pair(qmri_ctx* ctx, const TcConvParams& p) {
     k.partial = p.partial; k.tickets = p.tickets;
     k.S = p.S; k.H = p.H; k.W = p.W; k.Cin = p.Cin; k.Cout = p.Cout;
     k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
-    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr; k.cluster_splitk = 0;
+    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr; k.cluster_splitk = 0; k.dual = 0; k.resw = 0;
     if (p.Cout == 64) return launch_pair<128, 1>(ctx, p, k);
     if (p.Cout == 128) return launch_pair<256, 1>(ctx, p, k);
     return launch_pair<256, 0>(ctx, p, k);
