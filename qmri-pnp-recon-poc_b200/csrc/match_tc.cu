@@ -13,9 +13,10 @@
 //
 // Kernel: persistent, warp-specialised.  Work item = (tile of 128 pixels, atom range).  Warp 0 (TMA): the pixel tile (real and
 // imaginary K-major rows, 2 x 16 KB, loaded once per work item) and a ring of 128-atom tiles (16 KB each) into 128B-swizzled
-// shared memory.  Warp 1 (MMA): per atom tile 2 x 4 tcgen05.mma (M128 x N128 x K8) into one of two TMEM accumulator pairs.
-// Warps 2-5 (epilogue; QMRI_K2_EPI_WARPS=8: warps 2-9, two per TMEM lane quarter, each taking 64 of the tile's 128 atom
-// columns - measured no faster): thread = pixel; tcgen05.ld of
+// shared memory.  Warp 1 and the last warp (MMA): per atom tile 4 tcgen05.mma (M128 x N128 x K8) each into one of two TMEM accumulator
+// pairs - warp 1 the real part, the last warp the imaginary part (one thread issues an MMA every ~103 cycles at best).
+// Warps 2-5 (epilogue; warps 2-9 for atom ranges >= 65 536: two per TMEM lane quarter, each taking 64 of the tile's 128 atom
+// columns): thread = pixel; tcgen05.ld of
 // the real and imaginary accumulators (issued one 32-column chunk ahead of the arithmetic), s = re^2 + im^2, the maximum of each
 // 16-atom group as a depth-4 tree (3 FP32 instructions per score; with one or two warps per scheduler a 16-long dependent
 // FMNMX chain was the limiter: ncu showed the epilogue warps issuing 41 % of the cycles).  The thread keeps the TWO BEST GROUPS
@@ -45,7 +46,7 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int MT_THREADS_MAX = 64 + 32 * 8;    // TMA warp + MMA warp + 4 or 8 epilogue warps (EW)
+constexpr int MT_THREADS_MAX = 96 + 32 * 8;    // TMA warp + MMA warp + 4 or 8 epilogue warps (EW) + second MMA warp
 constexpr int MT_BM = 128;                  // pixels per tile
 constexpr int MT_BN = 128;                  // atoms per tile
 constexpr int MT_KF = 32;                   // floats per operand row (128 B = one swizzle row)
@@ -64,6 +65,8 @@ struct MtParams {
     int64_t a0, a1;      // atoms scored: tile t of the packed matrix holds atoms a0 + 128 t ...
     int ntiles;          // atom tiles of the packed matrix
     int nsplit;          // atom-range splits per pixel tile
+    int issuers;         // MMA-issuing warps for complex pixels: 2 (default) or 1
+    int debug;           // profiling only (QMRI_K2_DEBUG): 1 = epilogue skips reads and arithmetic, 2 = MMA warp skips the MMAs
     int ptiles;
     int CP;
     unsigned long long* keys;
@@ -100,7 +103,7 @@ __global__ void match_prep_kernel(const float* __restrict__ x_re, const float* _
 }
 
 template <int C, bool CPLX, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1) match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(96 + 32 * EW, 1) match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                 const MtParams p) {
     extern __shared__ unsigned char mt_smem_raw[];
     const uint32_t raw = smem_u32(mt_smem_raw);
@@ -119,15 +122,20 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) match_tc_kernel(const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_work = p.ptiles * p.nsplit;
 
+    // Two MMA-issuing warps for complex pixels: one thread gets a tcgen05.mma out every ~103 cycles at best (profiles/r02_tmem_a_bench.txt),
+    // and the real and the imaginary accumulator are independent - warp 1 issues the real part's MMAs, the last warp the imaginary
+    // part's.  Both commit on the stage / accumulator / pixel-tile barriers (count 2).  QMRI_K2_ISSUERS=1 keeps a single issuer.
+    const bool two = CPLX && p.issuers == 2;
     if (threadIdx.x == 0) {
+        const uint32_t ni = two ? 2u : 1u;
         for (int s = 0; s < MT_STAGES; ++s) {
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
+            mbar_init(&b_empty[s], ni);
         }
         mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
+        mbar_init(a_empty, ni);
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull[a], 1);
+            mbar_init(&tfull[a], ni);
             mbar_init(&tempty[a], EW);
         }
         fence_barrier_init();
@@ -164,9 +172,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) match_tc_kernel(const __grid_
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+    } else if (warp == 1 || warp == 2 + EW) {
+        // ================= MMA issuer(s): warp 1 (real part; both parts with a single issuer), warp 2 + EW (imaginary part) =================
+        const bool second = warp != 1;
+        if (lane == 0 && (!second || two)) {
+            const bool do_re = !second, do_im = CPLX && (second || !two);
             // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MT_BN >> 3) << 17) | ((uint32_t)(MT_BM >> 4) << 24);
             const uint64_t a_re = umma_desc_sw128(smem_u32(smA)), a_im = umma_desc_sw128(smem_u32(smA + MT_A_PART));
@@ -186,16 +196,20 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) match_tc_kernel(const __grid_
                     tc_fence_after();
                     const uint64_t b = umma_desc_sw128(smem_u32(smB + (size_t)stage * MT_B_TILE));
                     const uint32_t d_re = tmem_base + (uint32_t)(ab * 2 * MT_BN), d_im = d_re + MT_BN;
+                    if (p.debug != 2) {
+                        if (do_re) {
 #pragma unroll
-                    for (int k = 0; k < MT_KF / 8; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes along K inside the swizzle row (16-byte units)
-                        mma_tf32_ss(d_re, a_re + ko, b + ko, idesc, k ? 1u : 0u);
-                    }
-                    if (CPLX) {
+                            for (int k = 0; k < MT_KF / 8; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes along K inside the swizzle row (16-byte units)
+                                mma_tf32_ss(d_re, a_re + ko, b + ko, idesc, k ? 1u : 0u);
+                            }
+                        }
+                        if (do_im) {
 #pragma unroll
-                        for (int k = 0; k < MT_KF / 8; ++k) {
-                            const uint64_t ko = (uint64_t)(k * 2);
-                            mma_tf32_ss(d_im, a_im + ko, b + ko, idesc, k ? 1u : 0u);
+                            for (int k = 0; k < MT_KF / 8; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 2);
+                                mma_tf32_ss(d_im, a_im + ko, b + ko, idesc, k ? 1u : 0u);
+                            }
                         }
                     }
                     tc_commit(&b_empty[stage]);
@@ -271,6 +285,16 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) match_tc_kernel(const __grid_
             for (int t = t0; t < t1; ++t, ++it) {
                 const int ab = it & 1;
                 const int gid = (t - t0) * (MT_BN / 16) + 2 * NCH * half;
+                if (p.debug == 1) {  // profiling: hand the buffer straight back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[ab]);
+                    if (t + 1 < t1) {
+                        mbar_wait(&tfull[(it + 1) & 1], ((it + 1) >> 1) & 1);
+                        tc_fence_after();
+                    }
+                    continue;
+                }
                 if (NCH == 4) {
                     load_chunk(tile_addr(it) + 32, reB, imB);
                     score_chunk(reA, imA, gid);
@@ -410,9 +434,16 @@ int launch_c(qmri_ctx* ctx, const K2TcDict& d, const K2Params& p, float* A, int6
         if (waves >= 6) break;
     }
     m.nsplit = nsplit;
+    static const int dbg = getenv("QMRI_K2_DEBUG") ? atoi(getenv("QMRI_K2_DEBUG")) : 0;  // attribution of the tile time: wrong results by design
+    m.debug = dbg;
+    static const int iss = getenv("QMRI_K2_ISSUERS") ? atoi(getenv("QMRI_K2_ISSUERS")) : 2;
+    m.issuers = iss == 1 ? 1 : 2;
     const int grid = (int)std::min<int64_t>((int64_t)m.ptiles * nsplit, ctx->sm_count);
-    static const int ew_env = getenv("QMRI_K2_EPI_WARPS") ? atoi(getenv("QMRI_K2_EPI_WARPS")) : 0;  // tuning knob: 4 or 8
-    const int ew = ew_env == 8 ? 8 : 4;
+    // Epilogue warps: 8 (two per TMEM lane quarter) once the MMA side has two issuers and the atom range is long, 4 otherwise; measured on
+    // the benchmark's dictionary, two issuers: 10 000 / 100 000 / 1 048 576 atoms: 4 warps 1.98 / 3.02 / 3.26, 8 warps 1.65 / 3.15 / 3.46
+    // x 10^12 px-atoms/s (profiles/r02o_k2_issuers.txt).  QMRI_K2_EPI_WARPS=4|8 forces one.
+    static const int ew_env = getenv("QMRI_K2_EPI_WARPS") ? atoi(getenv("QMRI_K2_EPI_WARPS")) : 0;
+    const int ew = ew_env == 8 ? 8 : ew_env == 4 ? 4 : (p.x_im && m.issuers == 2 && (p.a1 - p.a0) >= 65536 ? 8 : 4);
     static bool configured_dev[QMRI_MAX_DEV][4] = {};
     bool& conf = configured_dev[qmri_dev_slot(ctx)][(p.x_im ? 1 : 0) + (ew == 8 ? 2 : 0)];
     const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(d.mapB);
@@ -420,7 +451,7 @@ int launch_c(qmri_ctx* ctx, const K2TcDict& d, const K2Params& p, float* A, int6
     do {                                                                                                                          \
         if (!conf) QCUDA(cudaFuncSetAttribute(match_tc_kernel<C, CPLX, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM)); \
         conf = true;                                                                                                              \
-        match_tc_kernel<C, CPLX, EW><<<grid, 64 + 32 * EW, MT_SMEM, ctx->stream>>>(tmA, tmB, m);                                  \
+        match_tc_kernel<C, CPLX, EW><<<grid, 96 + 32 * EW, MT_SMEM, ctx->stream>>>(tmA, tmB, m);                                  \
     } while (0)
     if (p.x_im) {
         if (ew == 8) MT_LAUNCH(true, 8);
