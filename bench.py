@@ -517,8 +517,7 @@ def run_ours(args, rank, world, local_rank):
     fwd_flops = net.flops(S, N_IMG, N_IMG)
     fwd_tflops = fwd_flops / (ms_per_fwd * 1e-3) / 1e12
     step_ms = ms_dev / args.steps
-    tkey = f"unetres_forward_S{min(S, 15) if S >= 15 else S}"
-    t_fwd = traffic.get(tkey)
+    t_fwd = traffic.get(f"unetres_forward_S{S}") or traffic.get(f"unetres_forward_S{min(S, 15) if S >= 15 else S}")   # exact slice count first
     max_chunk = int(os.environ.get("QMRI_NET_CHUNK", "128"))   # unetres.h max_chunk: slices per pass through the network
     chunks = -(-S // max_chunk)
     per_chunk = -(-S // chunks)

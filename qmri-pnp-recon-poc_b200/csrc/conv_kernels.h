@@ -73,4 +73,7 @@ int conv_tc(qmri_ctx* ctx, const TcConvParams& p);
 int tc_slab_tile_shape(int W, int H, int* BW, int* BH);
 void tc_pair_weight_boxes(int Cout, int* rows_main, int* rows_h2);
 int conv3x3_tc_pair(qmri_ctx* ctx, const TcConvParams& p);
+// operand-swapped 64 -> 64 conv (weights in TMEM, 224 pixels as the MMA's N): mapA_*[0] = activation maps with box (16, 16)
+bool conv64_swap_supported(int W, int H, int Cin, int Cout);
+int conv64_swap(qmri_ctx* ctx, const TcConvParams& p, const uint16_t* w_hi, const uint16_t* w_lo);
 int normalize_planar(qmri_ctx* ctx, const float* in, float* out, const float* minmax, size_t per_slice, int S, int undo);

@@ -1410,6 +1410,280 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
     return QMRI_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Operand-swapped 3x3 conv for the 64 -> 64 layers (Cin = Cout = 64).
+//
+// One thread issues a tcgen05.mma every ~103 cycles at best whatever its N (profiles/r02_tmem_a_bench.txt), so a layer whose GEMM
+// has only N = 64 output channels (128 with the hi / lo weight planes stacked) cannot feed the tensor pipe from the N side.  Here the
+// roles are swapped: the stacked weights [w_hi ; w_lo] are the M = 128 A operand and live in TENSOR MEMORY for the whole kernel
+// (576 bf16 per row = 288 columns, written once per CTA with tcgen05.st), the PIXELS are the N dimension - 224 of them per tile (14
+// rows x 16), the widest N the remaining 224 TMEM columns allow for the accumulator - and only the activation slabs stream through
+// shared memory.  Per K step two N = 224 MMAs (B = the hi and the lo activation plane; row 2 c of D collects w_hi[c] (a_hi + a_lo),
+// row 2 c + 1 w_lo[c] (a_hi + a_lo) - the fourth product a_lo w_lo comes for free).  The accumulator is single-buffered; the epilogue
+// therefore drains it quickly (tcgen05.ld, the hi / lo rows of a channel meet through one lane shuffle, the tile goes to shared
+// memory as [channel][pixel] fp32) and hands it back, and the slow part - residual, ReLU, hi-lo split, 16-byte stores - runs from
+// shared memory while the next tile's MMAs are under way.
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_BW = 16, SW_BH = 14, SW_N = SW_BW * SW_BH;              // 224 pixels per tile
+constexpr int SW_STAGES = 2;
+constexpr uint32_t SW_PLANE = (SW_BH + 2) * SW_BW * 128;                  // 32 KB: (14 + 2) x 16 rows of 128 B
+constexpr uint32_t SW_STAGE = 2 * SW_PLANE;                               // hi + lo
+constexpr size_t SW_SMEM = (size_t)SW_STAGES * SW_STAGE + 64 * SW_N * 4 /*the finished tile, [channel][pixel] fp32*/ + 1024 + 256;
+constexpr uint32_t SW_ACOL = 224;                                         // TMEM: D in columns [0, 224), weights in [224, 512)
+
+struct SwapK {
+    uint16_t *out_hi, *out_lo;
+    const uint16_t *res1_hi, *res1_lo, *res2_hi, *res2_lo;
+    const uint16_t *w_hi, *w_lo;   // [64][576] K-major (tap-major, then input channel)
+    int S, H, W, tiles_x, tiles_y, relu;
+};
+
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+        "%23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+          "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+        "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the four epilogue warps
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv64_swap_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const SwapK p) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    float* tile = reinterpret_cast<float*>(smem + (size_t)SW_STAGES * SW_STAGE);   // [64 channels][224 pixels]; pixel j of a 32-pixel chunk of
+                                                                                    // channel c sits at (j + c) & 31 (bank-conflict-free both ways)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tile + 64 * SW_N);
+    uint64_t* full = bars;                  // [SW_STAGES]
+    uint64_t* empty = bars + SW_STAGES;     // [SW_STAGES]
+    uint64_t* dfull = bars + 2 * SW_STAGES; // accumulator complete
+    uint64_t* dempty = dfull + 1;           // accumulator drained (4 epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_xy = p.tiles_x * p.tiles_y;
+    const int ntiles = tiles_xy * p.S;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SW_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(dfull, 1);
+        mbar_init(dempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&tmA_hi);
+        tma_prefetch_desc(&tmA_lo);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int lg = warp & 3;  // TMEM lane quarter of an epilogue warp (warps 2-5 -> quarters 2, 3, 0, 1)
+    if (warp >= 2) {
+        // the layer's weights into TMEM: lane 2 c = w_hi[c], lane 2 c + 1 = w_lo[c]; 288 columns of bf16 pairs
+        const int r = lg * 32 + lane;
+        const uint4* src = reinterpret_cast<const uint4*>(((r & 1) ? p.w_lo : p.w_hi) + (size_t)(r >> 1) * 576);
+#pragma unroll 1
+        for (int c = 0; c < 9; ++c) {
+            uint32_t v[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 t = __ldg(src + c * 8 + q);
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            tc_st32(tmem_base + ((uint32_t)(lg * 32) << 16) + SW_ACOL + 32 * c, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_wait();  // everything below reads activations produced by earlier kernels
+
+    if (warp == 0) {
+        // ================= TMA producer: one (16 + 2... rows) x 16 slab pair per dx =================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
+                const int s = w / tiles_xy, txy = w - s * tiles_xy;
+                const int x0 = (txy % p.tiles_x) * SW_BW, y0 = (txy / p.tiles_x) * SW_BH;
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    unsigned char* sp = smem + (size_t)st * SW_STAGE;
+                    mbar_expect_tx(&full[st], SW_STAGE);
+                    tma_load_4d(sp, &tmA_hi, &full[st], 0, x0 + dxi - 1, y0 - 1, s);
+                    tma_load_4d(sp + SW_PLANE, &tmA_lo, &full[st], 0, x0 + dxi - 1, y0 - 1, s);
+                    if (++st == SW_STAGES) {
+                        st = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // D = f32, A = B = bf16, K-major, M = 128, N = 224
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SW_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t tmem_d = tmem_base, tmem_a = tmem_base + SW_ACOL;
+            int st = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int w = blockIdx.x; w < ntiles; w += gridDim.x, ++it) {
+                mbar_wait(dempty, (uint32_t)(it & 1) ^ 1);  // the epilogue has read the previous tile out of the accumulator
+                tc_fence_after();
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + (size_t)st * SW_STAGE);
+#pragma unroll
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        const uint64_t b_hi = umma_desc(sb + dyi * (SW_BW * 128)), b_lo = umma_desc(sb + SW_PLANE + dyi * (SW_BW * 128));
+                        const uint32_t a_tap = tmem_a + (uint32_t)((dyi * 3 + dxi) * 32);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            tc_mma_ts(tmem_d, a_tap + 8 * k, b_hi + (uint64_t)(2 * k), idesc, (dxi | dyi | k) ? 1u : 0u);
+                            tc_mma_ts(tmem_d, a_tap + 8 * k, b_lo + (uint64_t)(2 * k), idesc, 1u);
+                        }
+                    }
+                    tc_commit(&empty[st]);
+                    if (++st == SW_STAGES) {
+                        st = 0;
+                        ph ^= 1;
+                    }
+                }
+                tc_commit(dfull);
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int c = 16 * lg + (lane >> 1);   // output channel of this lane pair (even lane: w_hi part, odd lane: w_lo part)
+        const int pr = lane & 1;               // after the shuffle both lanes hold the sum; lane parity pr stores columns 16 pr .. 16 pr + 15
+        const int seg = warp - 2;              // store phase: warp = 16-channel segment, lane = pixel (mod 32)
+        int it = 0;
+        for (int w = blockIdx.x; w < ntiles; w += gridDim.x, ++it) {
+            const int s = w / tiles_xy, txy = w - s * tiles_xy;
+            const int x0 = (txy % p.tiles_x) * SW_BW, y0 = (txy / p.tiles_x) * SW_BH;
+            epi_bar();  // the previous tile's store phase has finished reading `tile`
+            mbar_wait(dfull, (uint32_t)(it & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < SW_N; c0 += 32) {
+                uint32_t a[32];
+                tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, a);
+                tc_wait_ld();
+                float* row = tile + c * SW_N + c0;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const float lo16 = __uint_as_float(a[t]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(a[t]), 1);
+                    const float hi16 = __uint_as_float(a[16 + t]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(a[16 + t]), 1);
+                    row[(16 * pr + t + c) & 31] = pr ? hi16 : lo16;
+                }
+            }
+            // the accumulator has been read out: the next tile's MMAs may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dempty);
+            epi_bar();  // `tile` is complete
+#pragma unroll 1
+            for (int q = 0; q < SW_N / 32; ++q) {
+                const int n = 32 * q + lane;
+                const int x = x0 + (n & 15), y = y0 + (n >> 4);
+                if (x < p.W && y < p.H) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int co = 16 * seg + i;
+                        v[i] = tile[co * SW_N + 32 * q + ((lane + co) & 31)];
+                    }
+                    const size_t o = (((size_t)s * p.H + y) * p.W + x) * 64 + 16 * seg;
+                    if (p.res1_hi) {
+                        const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o);
+                        const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o);
+                        add_split8(v, gh[0], gl[0]);
+                        add_split8(v + 8, gh[1], gl[1]);
+                    }
+                    if (p.res2_hi) {
+                        const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o);
+                        const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o);
+                        add_split8(v, gh[0], gl[0]);
+                        add_split8(v + 8, gh[1], gl[1]);
+                    }
+                    store_split16(p.out_hi + o, p.out_lo + o, v, p.relu);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// Host side: mapA_*[0] = activation maps with box (16 px, 16 rows) of 64 channels; w_hi / w_lo = the layer's raw K-major weight planes.
+bool conv64_swap_supported(int W, int H, int Cin, int Cout) { return Cin == 64 && Cout == 64 && W % SW_BW == 0 && H % SW_BH == 0; }
+int conv64_swap(qmri_ctx* ctx, const TcConvParams& p, const uint16_t* w_hi, const uint16_t* w_lo) {
+    if (!conv64_swap_supported(p.W, p.H, p.Cin, p.Cout)) return qmri_fail(QMRI_EINVAL, "conv64_swap: %d x %d, %d -> %d channels", p.W, p.H, p.Cin, p.Cout);
+    if (!p.mapA_hi[0] || !p.mapA_lo[0] || !w_hi || !w_lo) return qmri_fail(QMRI_EINVAL, "conv64_swap: missing tensor map / weights");
+    static bool configured_dev[QMRI_MAX_DEV] = {};
+    bool& configured = configured_dev[qmri_dev_slot(ctx)];
+    if (!configured) {
+        QCUDA(cudaFuncSetAttribute(tc_conv64_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+        configured = true;
+    }
+    SwapK k;
+    k.out_hi = p.out_hi; k.out_lo = p.out_lo;
+    k.res1_hi = p.res1_hi; k.res1_lo = p.res1_lo;
+    k.res2_hi = p.res2_hi; k.res2_lo = p.res2_lo;
+    k.w_hi = w_hi; k.w_lo = w_lo;
+    k.S = p.S; k.H = p.H; k.W = p.W;
+    k.tiles_x = p.W / SW_BW; k.tiles_y = p.H / SW_BH;
+    k.relu = p.relu;
+    const int ntiles = k.tiles_x * k.tiles_y * p.S;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = SW_SMEM;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tc_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QCUDA(cudaLaunchKernelEx(&cfg, tc_conv64_swap_kernel, *(const CUtensorMap*)p.mapA_hi[0], *(const CUtensorMap*)p.mapA_lo[0], (const SwapK)k));
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+
 // 3x3 conv through the CTA-pair kernel.  mapA_*[0]: activation maps with box (BW, BH + 2); mapB_hi / mapB_lo / mapB_h2:
 // weight maps with the box rows of tc_pair_weight_boxes().
 int conv3x3_tc_pair(qmri_ctx* ctx, const TcConvParams& p) {

@@ -351,6 +351,10 @@ static int build_act_maps(qmri_net* net, int H, int W) {
             tc_slab_tile_shape(W >> l, H >> l, &SW, &SH);
             QCHECK(tc_make_act_map(&net->amap_slab[b][l][0], hi[b][l], net->chunk, H >> l, W >> l, NC[l], SW, SH + 2));
             QCHECK(tc_make_act_map(&net->amap_slab[b][l][1], lo[b][l], net->chunk, H >> l, W >> l, NC[l], SW, SH + 2));
+            if (l == 0 && conv64_swap_supported(W, H, NC[0], NC[0])) {
+                QCHECK(tc_make_act_map(&net->amap_swap[b][0], hi[b][0], net->chunk, H, W, NC[0], 16, 16));
+                QCHECK(tc_make_act_map(&net->amap_swap[b][1], lo[b][0], net->chunk, H, W, NC[0], 16, 16));
+            }
             if (l < 3) {  // stride-2 tap views feeding the down conv to level l + 1
                 int DW, DH;
                 tc_tile_shape(W >> (l + 1), H >> (l + 1), &DW, &DH);
@@ -440,6 +444,15 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
         tiles(p);
         // CTA-pair kernel when the layer fills the machine with pair tiles; the single-CTA kernel (finer tiles, split-K)
         // for the small layers of small slice batches, which are latency- rather than throughput-bound
+        {
+            // operand-swapped kernel for the 64 -> 64 layers of a batch that fills the machine (one 224-pixel tile per CTA at least)
+            const char* sw_env = getenv("QMRI_TC_SWAP");  // read per call: tests toggle it.  Off by default: measured on par with the pair
+            const bool sw_on = sw_env ? atoi(sw_env) != 0 : net->tc_swap != 0;  // kernel (profiles/r02_conv64_experiments.md)
+            if (lvl == 0 && sw_on && conv64_swap_supported(p.W, p.H, p.Cin, p.Cout) && (p.W / 16) * (p.H / 14) * S >= ctx->sm_count) {
+                p.mapA_hi[0] = &net->amap_swap[src][0]; p.mapA_lo[0] = &net->amap_swap[src][1];
+                return conv64_swap(ctx, p, net->wtc_hi[orient][layer], net->wtc_lo[orient][layer]);
+            }
+        }
         int SW, SH;
         tc_slab_tile_shape(p.W, p.H, &SW, &SH);
         const int pair_groups = ((((p.W + SW - 1) / SW) * ((p.H + SH - 1) / SH) * S + 1) / 2) * (NC[lvl] >= 256 ? NC[lvl] / 256 : 1);

@@ -301,6 +301,25 @@ def test_denoiser_chunked_passes_equal_single_pass(q, monkeypatch):
     assert rel_l2(y3[..., 4], ref) <= TOL_DENOISER
 
 
+def test_denoiser_operand_swapped_64_channel_kernel(q, monkeypatch):
+    """QMRI_TC_SWAP=1: the 64 -> 64 convs run through the operand-swapped kernel (weights resident in TMEM as the MMA's A operand,
+    224 pixels as its N; csrc/conv_tc.cu conv64_swap) - same result as the CTA-pair kernel, within the denoiser tolerance of the CPU forward."""
+    from oracle import unetres
+    sd = unetres.make_state_dict(10, seed=0)
+    rng = np.random.default_rng(6)
+    A = rng.random((224, 224, 10, 3))
+    net = q.UNetRes(sd, in_nc=10)
+    net.set_precision("tc")
+    ctx = q.Context.default()
+    y_pair = net.denoise(A)
+    monkeypatch.setenv("QMRI_TC_SWAP", "1")
+    l0 = ctx.launch_count
+    y_swap = net.denoise(A)
+    assert ctx.launch_count - l0 >= 64
+    assert rel_l2(y_swap, y_pair) <= 1e-5    # measured 4.4e-6: other summation order, the a_lo w_lo term on top (tensor mode itself: 5e-6 from the CPU forward)
+    assert rel_l2(y_swap[..., 1], unetres.denoise_matlab_layout(sd, A[..., 1])) <= TOL_DENOISER
+
+
 def test_denoiser_multi_level_11_channels(q):
     import torch
     from oracle import unetres
