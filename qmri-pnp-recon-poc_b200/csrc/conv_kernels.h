@@ -56,6 +56,11 @@ struct TcConvParams {
     const void* mapB_hi;       // weights [N][K] K-major, box = tc_block_n(Cout) rows
     const void* mapB_lo;
     const void* mapB_h2;       // pair kernel, stacked mode: w_hi with a box of Cout / 2 rows
+    const void* mapB_l2;       // pair kernel, resident-weight mode: w_lo with a box of Cout / 2 rows
+    const void* mapO_hi;       // pair kernel, 64 -> 64 layers: OUTPUT maps with box (BW, BH) for the bulk tensor stores of the epilogue
+    const void* mapO_lo;
+    const void* mapR_hi;       // ... and the same kind of maps over the res1 buffer (residual tile by bulk tensor load)
+    const void* mapR_lo;
 };
 
 int conv3x3_fp32(qmri_ctx* ctx, const ConvParams& p);

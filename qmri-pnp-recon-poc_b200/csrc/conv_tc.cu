@@ -184,7 +184,15 @@ struct TcK {
     int cluster_splitk;  // split-K partials meet in the shared memory of a thread-block cluster of nsplit CTAs (one work item per CTA)
     int dual;            // CTA-pair kernel, Cout = 64: a second warp issues the a_lo w_hi MMAs into their own accumulator columns
     int resw;            // CTA-pair kernel, Cin = Cout = 64: the layer's weights stay resident in shared memory
+    int tma_out;         // CTA-pair kernel, resw layers: the output tile leaves through shared memory + bulk tensor stores
+    int res_tma;         // ... and the ResBlock residual tile arrives in the same staging tile through a bulk tensor load
+    unsigned long long* prof;  // QMRI_TC_PROF: per-CTA cycle counters of the pair kernel's roles (8 per CTA), else null
 };
+
+// role-level attribution (QMRI_TC_PROF=1): cycles a role spends inside a wait, accumulated per CTA
+#define TC_PROF_T0() const long long prof_t0 = p.prof ? clock64() : 0
+#define TC_PROF_ADD(var) do { if (p.prof) (var) += (unsigned long long)(clock64() - prof_t0); } while (0)
+#define TC_PROF_PUT(slot, val) do { if (p.prof) p.prof[blockIdx.x * 16 + (slot)] = (unsigned long long)(val); } while (0)
 
 #define TC_TRACE(slot, val)                                                   \
     do {                                                                      \
@@ -229,6 +237,36 @@ __device__ __forceinline__ void store_split16(uint16_t* oh, uint16_t* ol, const 
     o4l[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     o4l[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
 }
+
+// ReLU, split to (hi, lo) and park 16 consecutive channels (two 16-byte chunks per plane) of tile row `r` in a shared-memory
+// tile of 128-byte rows laid out as TMA SWIZZLE_128B expects (chunk j of row r at position j ^ (r & 7)): conflict-free for a
+// warp (8 consecutive rows hit 8 different chunk columns), and one bulk tensor store then writes whole 128-byte lines.
+__device__ __forceinline__ void store_split16_smem(uint32_t hi_row, uint32_t lo_row, int chunk0, int r7, const float* v, int relu) {
+    uint32_t ph[8], pl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a = v[2 * j], b = v[2 * j + 1];
+        if (relu) {
+            a = fmaxf(a, 0.f);
+            b = fmaxf(b, 0.f);
+        }
+        ph[j] = pack_bf16(a, b);
+        float ha, hb;
+        unpack_bf16(ph[j], ha, hb);
+        pl[j] = pack_bf16(a - ha, b - hb);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t off = (uint32_t)(((chunk0 + h) ^ r7) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_row + off), "r"(ph[4 * h]), "r"(ph[4 * h + 1]), "r"(ph[4 * h + 2]), "r"(ph[4 * h + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_row + off), "r"(pl[4 * h]), "r"(pl[4 * h + 1]), "r"(pl[4 * h + 2]), "r"(pl[4 * h + 3]) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void epi_bar128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the four epilogue warps of a CTA
 
 // Epilogue of one 128 x BN tile (no split-K).  This thread owns one output pixel (TMEM lane) and BN
 // channels.  The ResBlock residual of the pixel (BN hi + BN lo bf16 = BN/4 uint4) is fetched into
@@ -644,10 +682,13 @@ struct PairCfg {
     static constexpr uint32_t B2_BYTES = STACK ? (NA / 4) * 128 : B1_BYTES;  // STACK: half of the N = NA/2 operand; else the lo plane
     static constexpr uint32_t B_STAGE = B1_BYTES + B2_BYTES;
     static constexpr int AS = (NA == 128) ? 3 : 2;
+    static constexpr int ASB = 4;                                // slab-stage barrier slots (resident-weight mode runs up to four stages)
     static constexpr int BS = (NA == 128) ? 8 : (STACK ? 5 : 4);
     static constexpr bool DUAL_OK = STACK && NA == 128;          // room in TMEM for a separate accumulator of the a_lo w_hi product
     static constexpr uint32_t TMEM_COLS = DUAL_OK ? 512 : 2 * NA; // two accumulators (+ 2 x NA/2 columns for the second issuer's)
-    static constexpr size_t SMEM = (size_t)AS * A_SLOT + (size_t)BS * B_STAGE + 1024 + 256;
+    static constexpr uint32_t RESW_BYTES = 9 * B1_BYTES;         // resident-weight mode: nine taps of this CTA's 64 stacked weight rows
+    static constexpr size_t STAGE_AREA = (size_t)AS * A_SLOT + (size_t)BS * B_STAGE;
+    static constexpr size_t SMEM = STAGE_AREA + 1024 + 256;
 };
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
@@ -684,14 +725,38 @@ __device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t desc_a, uint64
         : "memory");
 }
 
+// Warp-converged forms: the WHOLE warp runs the issue loop and one elected lane executes the instruction.  With the loop inside
+// `if (lane == 0)` ptxas cannot keep descriptors / addresses in uniform registers and wraps every UTCHMMA in an ELECT + 5 x
+// R2UR.BROADCAST + BRA.U.ANY "waterfall" loop - that loop, not the hardware, was the ~103-cycle-per-MMA "issue floor" of
+// profiles/r02_tmem_a_bench.txt (profiles/r02u_pair_roles.md).
+__device__ __forceinline__ void tc2_mma_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc2_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
+
 // 16 consecutive output channels of this thread's pixel from the accumulator (STACK: sum of the two column blocks)
+// resw (resident-weight layout of the 64 -> 64 layers): the accumulator columns are [hi(0-31) | lo(32-63) | hi(32-63) | lo(0-31)]
+// (+ a_lo w_hi(c) added onto column c), so the second term of channel c sits at column c + 96 (c < 32) or c + 32 (c >= 32)
 template <int NA, int STACK>
-__device__ __forceinline__ void pair_acc16(uint32_t taddr, uint32_t taddr2, int c0, float* v) {
+__device__ __forceinline__ void pair_acc16(uint32_t taddr, uint32_t taddr2, int c0, float* v, bool resw = false) {
     uint32_t a[16];
     tc_ld16(taddr + c0, a);
     if (STACK) {
         uint32_t b[16];
-        tc_ld16(taddr + NA / 2 + c0, b);
+        tc_ld16(taddr + (resw ? (c0 < NA / 4 ? 3 * NA / 4 : NA / 4) : NA / 2) + c0, b);
         if (taddr2) {  // dual-issuer mode: a_lo w_hi was accumulated in its own columns
             uint32_t c[16];
             tc_ld16(taddr2 + c0, c);
@@ -714,7 +779,9 @@ template <int NA, int STACK>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                       const __grid_constant__ CUtensorMap tmB_h2, const TcK p) {
+                       const __grid_constant__ CUtensorMap tmB_h2, const __grid_constant__ CUtensorMap tmB_l2,
+                       const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+                       const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo, const TcK p) {
     using Cfg = PairCfg<NA, STACK>;
     constexpr int AS = Cfg::AS, BS = Cfg::BS, NOUT = Cfg::NOUT;
     extern __shared__ unsigned char tc_smem_raw[];
@@ -722,15 +789,16 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     unsigned char* smemB = smem + (size_t)AS * Cfg::A_SLOT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)BS * Cfg::B_STAGE);
+    constexpr int ASB = Cfg::ASB;
     uint64_t* fullA = bars;               // leader's are used
-    uint64_t* emptyA = bars + AS;         // per CTA
-    uint64_t* fullB = bars + 2 * AS;      // leader's
-    uint64_t* emptyB = bars + 2 * AS + BS;
-    uint64_t* tfull = bars + 2 * AS + 2 * BS;  // per CTA
+    uint64_t* emptyA = bars + ASB;        // per CTA
+    uint64_t* fullB = bars + 2 * ASB;     // leader's
+    uint64_t* emptyB = bars + 2 * ASB + BS;
+    uint64_t* tfull = bars + 2 * ASB + 2 * BS;  // per CTA
     uint64_t* tempty = tfull + 2;              // leader's
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shuffle: tells ptxas the warp index is warp-uniform
     const int cblocks = p.Cin / TC_BK;
     const int U = 3 * cblocks;                                // K units: (channel block, dx); each = 1 slab + 3 weight tiles
     const int NT = p.Cout / NOUT;
@@ -746,18 +814,39 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     // (profiles/r02_tmem_a_bench.txt), so the two MMAs of a K step - N = 128 and N = 64, 96 cycles of tensor time - took ~206.  Warp 1
     // keeps a_hi x [w_hi | w_lo]; warp 6 issues a_lo x w_hi into its OWN accumulator columns (MMAs of different threads are not ordered
     // against each other, so they must not share an accumulator); the epilogue adds the third block.
-    const bool dual = Cfg::DUAL_OK && p.dual;
+    const bool dual = Cfg::DUAL_OK && (p.dual & 1);
     // Resident-weight mode (Cin = Cout = 64 layers).  With Cout = 64 a 128-pixel tile re-streamed the whole layer's weights (108 KB per
     // CTA: nine taps of [w_hi ; w_lo] and w_hi) next to 120 KB of activation slabs - 66 B/clk per SM at the tensor rate against the
-    // ~43 B/clk an SM gets from L2 through TMA.  Here the nine weight tiles are loaded ONCE per CTA into the space of the weight ring and
-    // the third slab stage; the main loop streams activation slabs only (two stages).
+    // ~43 B/clk an SM gets from L2 through TMA.  Here the nine weight tiles are loaded ONCE per CTA and the main loop streams activation
+    // slabs only.  Per tap a CTA keeps 64 rows: CTA 0 [w_hi(0-31) ; w_lo(32-63)], CTA 1 [w_hi(32-63) ; w_lo(0-31)].  The N = 128 MMA
+    // a_hi x B then leaves [hi(0-31) | lo(32-63) | hi(32-63) | lo(0-31)] in the accumulator columns, and the N = 64 MMA a_lo x (the
+    // FIRST 32 rows of each CTA, same descriptor) adds a_lo w_hi(c) onto column c for all 64 channels - no second copy of w_hi, 72 KB
+    // instead of 108 KB, which leaves room for three or four slab stages (two were measured to starve the MMA warp: a 40 KB stage is
+    // consumed in ~1400 cycles, less than its fetch takes under load).
     const bool resw = Cfg::DUAL_OK && p.resw && p.Cin == TC_BK;
-    const int AS_EFF = resw ? 2 : AS;
-    unsigned char* smemW = smem + (size_t)2 * Cfg::A_SLOT;   // resw: nine B_STAGE-sized weight tiles, tap-major
+    const uint32_t a_stage = resw ? 2 * slab_bytes : Cfg::A_SLOT;     // bytes per slab stage (hi + lo)
+    const uint32_t a_plane = resw ? slab_bytes : Cfg::A_PLANE;        // offset of the lo plane inside a stage
+    // resw + p.tma_out: the finished tile (128 pixel rows x 64 channels, hi and lo planes, 32 KB) is parked in shared memory and
+    // written with two bulk tensor stores - 16-byte stores of 32 lanes to 32 different lines made the epilogue the bound of the
+    // 64 -> 64 layers (one L2 request per lane and instruction: ~6400 cycles per tile, profiles/r02u_pair_roles.md)
+    // The staging tile is double-buffered, and for a layer with a ResBlock residual the producer warp first fills it with the
+    // residual tile (bulk tensor load): the epilogue reads its own row, adds, and writes the result back in place.
+    const bool tma_out = resw && p.tma_out;
+    const bool res_tma = tma_out && p.res_tma;
+    constexpr uint32_t OUT_BYTES = 2 * TC_BM * 128;
+    const int as_fit = (int)((Cfg::STAGE_AREA - Cfg::RESW_BYTES - (tma_out ? 2 * OUT_BYTES : 0u)) / (2 * slab_bytes));
+    uint64_t* fullR = fullB + 2;   // [2]; resw mode uses fullB[0] only, so the weight-ring barriers (count 1) are free
+    uint64_t* emptyR = fullB + 4;  // [2]
+    uint64_t* outFull = fullB + 6; // [2], count 4: the epilogue warps have written the finished tile into the staging buffer
+    const int as_cap = (p.resw >= 2 && p.resw < Cfg::ASB) ? p.resw : Cfg::ASB;   // QMRI_TC_RESW=2 / 3: fewer stages (A/B measurements)
+    const int AS_EFF = resw ? (as_fit < as_cap ? as_fit : as_cap) : AS;
+    unsigned char* smemW = smem;                                      // resw: nine taps x 64 rows x 128 B
+    unsigned char* smemO = smem + Cfg::RESW_BYTES;                    // tma_out: two staging tiles, each hi plane then lo plane
+    unsigned char* smemA = resw ? smem + Cfg::RESW_BYTES + (tma_out ? 2 * OUT_BYTES : 0u) : smem;      // slab stages
 
     if (threadIdx.x == 0) {
         const uint32_t nissue = dual ? 2u : 1u;  // MMA issuers that commit on the stage / accumulator barriers
-        for (int s = 0; s < AS; ++s) {
+        for (int s = 0; s < ASB; ++s) {
             mbar_init(&fullA[s], 1);
             mbar_init(&emptyA[s], nissue);
         }
@@ -768,6 +857,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], nissue);
             mbar_init(&tempty[a], 8);  // 4 epilogue warps of each CTA
+            if (tma_out) mbar_init(&outFull[a], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmA_hi);
@@ -775,6 +865,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         tma_prefetch_desc(&tmB_hi);
         tma_prefetch_desc(&tmB_lo);
         tma_prefetch_desc(&tmB_h2);
+        tma_prefetch_desc(&tmB_l2);
+        tma_prefetch_desc(&tmO_hi);
+        tma_prefetch_desc(&tmO_lo);
+        tma_prefetch_desc(&tmR_hi);
+        tma_prefetch_desc(&tmR_lo);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS));
@@ -787,7 +882,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     cluster_sync_all();  // both CTAs' barriers are initialised and TMEM is allocated before any cross-CTA signal
     if (threadIdx.x == 0) TC_TRACE(7, -2);
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_wait();  // everything below reads activations / partials / tickets produced by earlier kernels
 
     if (warp == 0) {
@@ -795,13 +890,15 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         if (lane == 0) {
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
+            unsigned long long prof_w5 = 0;
+            int itp = 0;
             if (resw && cidx < total_work) {  // the layer's weights, once: completion on the leader's fullB[0]
-                if (crank == 0) mbar_expect_tx(&fullB[0], 2 * 9 * Cfg::B_STAGE);
+                if (crank == 0) mbar_expect_tx(&fullB[0], 2 * Cfg::RESW_BYTES);
                 const uint32_t barW = mapa_rank(smem_u32(&fullB[0]), 0);
                 for (int tap = 0; tap < 9; ++tap) {
-                    unsigned char* wp = smemW + (size_t)tap * Cfg::B_STAGE;
-                    tma2_load_2d(wp, crank == 0 ? &tmB_hi : &tmB_lo, barW, tap * p.Cin, 0);
-                    tma2_load_2d(wp + Cfg::B1_BYTES, &tmB_h2, barW, tap * p.Cin, crank * (NOUT / 2));
+                    unsigned char* wp = smemW + (size_t)tap * Cfg::B1_BYTES;
+                    tma2_load_2d(wp, &tmB_h2, barW, tap * p.Cin, crank * (NOUT / 2));
+                    tma2_load_2d(wp + Cfg::B1_BYTES / 2, &tmB_l2, barW, tap * p.Cin, (1 - crank) * (NOUT / 2));
                 }
             }
             for (int w = cidx; w < total_work; w += nclusters) {
@@ -817,12 +914,20 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 for (int u = u0; u < u1; ++u) {
                     const int cb = u / 3, dxi = u - 3 * cb;
                     TC_TRACE(0, (w << 12) | (u << 4) | 1);
-                    mbar_wait(&emptyA[sa], pa ^ 1);
-                    unsigned char* st = smem + (size_t)sa * Cfg::A_SLOT;
+                    {
+                        TC_PROF_T0();
+                        mbar_wait(&emptyA[sa], pa ^ 1);
+                        TC_PROF_ADD(prof_w5);
+                    }
+                    unsigned char* st = smemA + (size_t)sa * a_stage;
+                    if (p.dual & 256) {  // timing experiment: no slab traffic, the stage is declared full at once
+                        if (crank == 0) mbar_arrive(&fullA[sa]);
+                    } else {
                     if (crank == 0) mbar_expect_tx(&fullA[sa], 4 * slab_bytes);  // both CTAs' hi + lo slabs
                     const uint32_t barA = mapa_rank(smem_u32(&fullA[sa]), 0);
                     tma2_load_4d(st, &tmA_hi, barA, cb * TC_BK, x0 + dxi - 1, y0 - 1, s);
-                    tma2_load_4d(st + Cfg::A_PLANE, &tmA_lo, barA, cb * TC_BK, x0 + dxi - 1, y0 - 1, s);
+                    tma2_load_4d(st + a_plane, &tmA_lo, barA, cb * TC_BK, x0 + dxi - 1, y0 - 1, s);
+                    }
                     if (++sa == AS_EFF) {
                         sa = 0;
                         pa ^= 1;
@@ -848,11 +953,21 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         }
                     }
                 }
+                if (res_tma) {  // after the tile's slabs: this CTA's residual tile into staging buffer itp & 1, once its previous bulk store has been read out
+                    const int rb = itp & 1;
+                    mbar_wait(&emptyR[rb], ((uint32_t)(itp >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(&fullR[rb], OUT_BYTES);
+                    unsigned char* rp = smemO + (size_t)rb * OUT_BYTES;
+                    tma_load_4d(rp, &tmR_hi, &fullR[rb], 0, x0, y0, s);
+                    tma_load_4d(rp + TC_BM * 128, &tmR_lo, &fullR[rb], 0, x0, y0, s);
+                }
+                ++itp;
             }
+            TC_PROF_PUT(5, prof_w5);
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (leader CTA only) =================
-        if (lane == 0 && crank == 0) {
+        // ================= MMA issuer (leader CTA only; the whole warp runs the loop, one elected lane issues) =================
+        if (crank == 0) {
             // instruction descriptors: D = f32, A = B = bf16, K-major, M = 256
             const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);
             const uint32_t idesc_full = idesc_base | ((uint32_t)(NA >> 3) << 17);
@@ -860,6 +975,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             int it = 0;
+            const long long role_t0 = p.prof ? clock64() : 0;
+            unsigned long long role_ns0 = 0;
+            if (p.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(role_ns0));
+            unsigned long long prof_w0 = 0, prof_w1 = 0, prof_n = 0, prof_w8 = 0, prof_w9 = 0;
             if (resw && cidx < total_work) {
                 mbar_wait(&fullB[0], 0);  // the resident weights have landed in both CTAs
                 tc_fence_after();
@@ -869,56 +988,110 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 const int u0 = (split * U) / p.nsplit, u1 = ((split + 1) * U) / p.nsplit;
                 const int ab = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
-                TC_TRACE(1, (w << 12) | 0xF00);
-                mbar_wait(&tempty[ab], aphase ^ 1);
+                if (lane == 0) TC_TRACE(1, (w << 12) | 0xF00);
+                {
+                    TC_PROF_T0();
+                    mbar_wait(&tempty[ab], aphase ^ 1);
+                    TC_PROF_ADD(prof_w1);
+                    ++prof_n;
+                }
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(ab * NA);
                 for (int u = u0; u < u1; ++u) {
-                    TC_TRACE(1, (w << 12) | (u << 4) | 1);
-                    mbar_wait(&fullA[sa], pa);
+                    if (lane == 0) TC_TRACE(1, (w << 12) | (u << 4) | 1);
+                    {
+                        TC_PROF_T0();
+                        mbar_wait(&fullA[sa], pa);
+                        TC_PROF_ADD(prof_w0);
+                    }
                     tc_fence_after();
-                    const uint32_t ha = smem_u32(smem + (size_t)sa * Cfg::A_SLOT);
+                    const uint32_t ha = smem_u32(smemA + (size_t)sa * a_stage);
+                    const long long issue_t0 = p.prof ? clock64() : 0;
                     for (int dyi = 0; dyi < 3; ++dyi) {
-                        TC_TRACE(1, (w << 12) | (u << 4) | (2 + dyi));
+                        if (lane == 0) TC_TRACE(1, (w << 12) | (u << 4) | (2 + dyi));
                         if (!resw) {
                             mbar_wait(&fullB[sb], pb);
                             tc_fence_after();
                         }
-                        const uint32_t sbase = resw ? smem_u32(smemW + (size_t)(dyi * 3 + (u - 3 * (u / 3))) * Cfg::B_STAGE)
+                        if (p.dual & 16) continue;  // timing experiment (QMRI_TC_DUAL=16): no MMAs at all
+                        const uint32_t sbase = resw ? smem_u32(smemW + (size_t)(dyi * 3 + (u - 3 * (u / 3))) * Cfg::B1_BYTES)
                                                     : smem_u32(smemB + (size_t)sb * Cfg::B_STAGE);
-                        const uint64_t a_hi = umma_desc(ha + dyi * dy_bytes), a_lo = umma_desc(ha + Cfg::A_PLANE + dyi * dy_bytes);
-                        const uint64_t b_1 = umma_desc(sbase), b_2 = umma_desc(sbase + Cfg::B1_BYTES);
+                        const uint64_t a_hi = umma_desc(ha + dyi * dy_bytes), a_lo = umma_desc(ha + a_plane + dyi * dy_bytes);
+                        const uint64_t b_1 = umma_desc(sbase), b_2 = umma_desc(resw ? sbase : sbase + Cfg::B1_BYTES);
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t ko = (uint64_t)(k * 2);
                             const uint32_t acc = ((u - u0) | dyi | k) ? 1u : 0u;
                             if (STACK) {
-                                tc2_mma(tmem_d, a_hi + ko, b_1 + ko, idesc_full, acc);   // [a_hi w_hi | a_hi w_lo]
-                                if (!dual) tc2_mma(tmem_d, a_lo + ko, b_2 + ko, idesc_half, 1u);    // += a_lo w_hi into the first block
+                                tc2_mma_elect(tmem_d, a_hi + ko, b_1 + ko, idesc_full, acc);   // [a_hi w_hi | a_hi w_lo]
+                                if (!dual) tc2_mma_elect(tmem_d, a_lo + ko, b_2 + ko, idesc_half, 1u);    // += a_lo w_hi into the first block
                             } else {
-                                tc2_mma(tmem_d, a_hi + ko, b_1 + ko, idesc_full, acc);
-                                tc2_mma(tmem_d, a_hi + ko, b_2 + ko, idesc_full, 1u);
-                                tc2_mma(tmem_d, a_lo + ko, b_1 + ko, idesc_full, 1u);
+                                tc2_mma_elect(tmem_d, a_hi + ko, b_1 + ko, idesc_full, acc);
+                                tc2_mma_elect(tmem_d, a_hi + ko, b_2 + ko, idesc_full, 1u);
+                                tc2_mma_elect(tmem_d, a_lo + ko, b_1 + ko, idesc_full, 1u);
                             }
                         }
                         if (!resw) {
-                            tc2_commit(&emptyB[sb]);  // frees the stage in both CTAs
+                            tc2_commit_elect(&emptyB[sb]);  // frees the stage in both CTAs
                             if (++sb == BS) {
                                 sb = 0;
                                 pb ^= 1;
                             }
                         }
                     }
-                    tc2_commit(&emptyA[sa]);
+                    if (p.prof) prof_w8 += (unsigned long long)(clock64() - issue_t0);
+                    {
+                        TC_PROF_T0();
+                        tc2_commit_elect(&emptyA[sa]);
+                        TC_PROF_ADD(prof_w9);
+                    }
                     if (++sa == AS_EFF) {
                         sa = 0;
                         pa ^= 1;
                     }
                 }
-                tc2_commit(&tfull[ab]);  // accumulator complete: wakes the epilogue warps of both CTAs
+                {
+                    TC_PROF_T0();
+                    tc2_commit_elect(&tfull[ab]);  // accumulator complete: wakes the epilogue warps of both CTAs
+                    TC_PROF_ADD(prof_w9);
+                }
+            }
+            if (lane == 0) {
+            TC_PROF_PUT(8, prof_w8);
+            TC_PROF_PUT(9, prof_w9);
+            TC_PROF_PUT(2, clock64() - role_t0);
+            }
+            if (p.prof && lane == 0) {
+                unsigned long long role_ns1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(role_ns1));
+                TC_PROF_PUT(6, role_ns1 - role_ns0);
+            }
+            if (lane == 0) {
+            TC_PROF_PUT(0, prof_w0);
+            TC_PROF_PUT(1, prof_w1);
+            TC_PROF_PUT(7, prof_n);
             }
         }
     } else if (warp == 6) {
+        // ================= store thread (64 -> 64 layers): finished tiles leave through bulk tensor stores =================
+        if (lane == 0 && tma_out) {
+            int it = 0;
+            for (int w = cidx; w < total_work; w += nclusters, ++it) {
+                const int pt = ((w / p.nsplit) / NT) * 2 + crank;
+                const int txy = pt % tiles_xy, s = pt / tiles_xy;
+                const int sbuf = it & 1;
+                mbar_wait(&outFull[sbuf], (uint32_t)(it >> 1) & 1u);
+                if (pt < ptiles && !(p.dual & 32)) {
+                    const int tx0 = (txy % p.tiles_x) * p.BW, ty0 = (txy / p.tiles_x) * p.BH;
+                    tma_store_4d(&tmO_hi, smem_u32(smemO) + (uint32_t)sbuf * OUT_BYTES, 0, tx0, ty0, s);
+                    tma_store_4d(&tmO_lo, smem_u32(smemO) + (uint32_t)sbuf * OUT_BYTES + TC_BM * 128u, 0, tx0, ty0, s);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer has been read out: hand it back
+                mbar_arrive(&emptyR[sbuf]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every bulk store of this CTA has completed
+        }
         // ================= second MMA issuer (leader CTA only, dual-issuer mode): a_lo x w_hi into its own accumulator =================
         if (lane == 0 && crank == 0 && dual) {
             const uint32_t idesc_half = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24) | ((uint32_t)((NA / 2) >> 3) << 17);
@@ -940,16 +1113,16 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 for (int u = u0; u < u1; ++u) {
                     mbar_wait(&fullA[sa], pa);
                     tc_fence_after();
-                    const uint32_t ha = smem_u32(smem + (size_t)sa * Cfg::A_SLOT);
+                    const uint32_t ha = smem_u32(smemA + (size_t)sa * a_stage);
                     for (int dyi = 0; dyi < 3; ++dyi) {
                         if (!resw) {
                             mbar_wait(&fullB[sb], pb);
                             tc_fence_after();
                         }
-                        const uint32_t sbase = resw ? smem_u32(smemW + (size_t)(dyi * 3 + (u - 3 * (u / 3))) * Cfg::B_STAGE)
+                        const uint32_t sbase = resw ? smem_u32(smemW + (size_t)(dyi * 3 + (u - 3 * (u / 3))) * Cfg::B1_BYTES)
                                                     : smem_u32(smemB + (size_t)sb * Cfg::B_STAGE);
-                        const uint64_t a_lo = umma_desc(ha + Cfg::A_PLANE + dyi * dy_bytes);
-                        const uint64_t b_2 = umma_desc(sbase + Cfg::B1_BYTES);
+                        const uint64_t a_lo = umma_desc(ha + a_plane + dyi * dy_bytes);
+                        const uint64_t b_2 = umma_desc(resw ? sbase : sbase + Cfg::B1_BYTES);
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t ko = (uint64_t)(k * 2);
@@ -977,6 +1150,8 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
         int it = 0;
+        const long long role_t0 = p.prof ? clock64() : 0;
+        unsigned long long prof_w3 = 0;
         for (int w = cidx; w < total_work; w += nclusters, ++it) {
             const int split = w % p.nsplit;
             const int r = w / p.nsplit;
@@ -996,48 +1171,136 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             const uint32_t tempty_leader = mapa_rank(smem_u32(&tempty[ab]), 0);
             if (lane == 0) TC_TRACE(2 + lg, (w << 12) | 1);
             if (p.nsplit == 1) {
-                // The ResBlock residual of this pixel is fetched into registers BEFORE waiting for the accumulator (up to 128
-                // channels at a time), so its latency hides behind the tile's MMA main loop.  tcgen05.ld is .sync.aligned:
-                // every lane of the warp executes it, only the memory accesses depend on `ok`.
-                constexpr int PRE = NOUT < 128 ? NOUT : 128;
-                const bool has_r1 = ok && (p.res1_hi != nullptr), has_r2 = ok && (p.res2_hi != nullptr);
-                uint4 rh[PRE / 8], rl[PRE / 8];
+                if constexpr (Cfg::DUAL_OK) {
+                    // ---- 64 -> 64 layers: lean epilogue.  The accumulator is drained 16 channels at a time with the tcgen05.ld of the
+                    // next chunk in flight; the ResBlock residual comes from the staging tile (filled by the producer's bulk tensor
+                    // load), the result goes back into the same row of that tile and leaves with two bulk tensor stores.  Without the
+                    // tile maps (tma_out off) residuals and outputs use 16-byte global accesses (slow, kept for A/B runs).
+                    const int sbuf = it & 1;
+                    const uint32_t suse = (uint32_t)(it >> 1);
+                    const uint32_t orow_hi = smem_u32(smemO) + (uint32_t)sbuf * OUT_BYTES + (uint32_t)row * 128u, orow_lo = orow_hi + TC_BM * 128u;
+                    const int r7 = row & 7;
+                    const bool g_r1 = ok && !res_tma && (p.res1_hi != nullptr), g_r2 = ok && (p.res2_hi != nullptr);
+                    uint4 q2[4];  // second residual (U-skip; last conv of a level only): global, fetched one chunk ahead
+                    if (g_r2) {
+                        q2[0] = *reinterpret_cast<const uint4*>(p.res2_hi + o);
+                        q2[1] = *reinterpret_cast<const uint4*>(p.res2_hi + o + 8);
+                        q2[2] = *reinterpret_cast<const uint4*>(p.res2_lo + o);
+                        q2[3] = *reinterpret_cast<const uint4*>(p.res2_lo + o + 8);
+                    }
+                    if (tma_out) {  // staging buffer: residual tile landed / previous bulk store of this buffer read out
+                        if (res_tma) mbar_wait(&fullR[sbuf], suse & 1u);
+                        else mbar_wait(&emptyR[sbuf], (suse & 1u) ^ 1u);
+                    }
+                    {
+                        TC_PROF_T0();
+                        mbar_wait(&tfull[ab], aphase);
+                        TC_PROF_ADD(prof_w3);
+                    }
+                    tc_fence_after();
+                    if (!(p.dual & 32)) {  // (QMRI_TC_DUAL=32, timing experiment: the epilogue only hands the accumulator back)
+                        uint32_t ta[2][16], tb[2][16];
+                        tc_ld16(taddr, ta[0]);
+                        tc_ld16(taddr + (resw ? 3 * NA / 4 : NA / 2), tb[0]);
 #pragma unroll
-                for (int h0 = 0; h0 < NOUT; h0 += PRE) {
-                    if (has_r1) {
-                        const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o + h0);
-                        const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o + h0);
+                        for (int ch = 0; ch < NOUT / 16; ++ch) {
+                            const int cc = 16 * ch, cur = ch & 1;
+                            tc_wait_ld();
+                            if (ch + 1 < NOUT / 16) {  // second term of channel c: column c + 96 (c < 32) or c + 32 (c >= 32), see pair_acc16
+                                const int cn = cc + 16;
+                                tc_ld16(taddr + cn, ta[cur ^ 1]);
+                                tc_ld16(taddr + (resw ? (cn < NA / 4 ? 3 * NA / 4 : NA / 4) : NA / 2) + cn, tb[cur ^ 1]);
+                            }
+                            float v[16];
 #pragma unroll
-                        for (int i = 0; i < PRE / 8; ++i) {
-                            rh[i] = gh[i];
-                            rl[i] = gl[i];
+                            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(ta[cur][j]) + __uint_as_float(tb[cur][j]);
+                            if (res_tma) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint32_t off = (uint32_t)((((cc >> 3) + h) ^ r7) << 4);
+                                    uint4 rh, rl;
+                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rh.x), "=r"(rh.y), "=r"(rh.z), "=r"(rh.w) : "r"(orow_hi + off));
+                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rl.x), "=r"(rl.y), "=r"(rl.z), "=r"(rl.w) : "r"(orow_lo + off));
+                                    add_split8(v + 8 * h, rh, rl);
+                                }
+                            } else if (g_r1) {
+                                const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o + cc);
+                                const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o + cc);
+                                add_split8(v, gh[0], gl[0]);
+                                add_split8(v + 8, gh[1], gl[1]);
+                            }
+                            if (g_r2) {
+                                add_split8(v, q2[0], q2[2]);
+                                add_split8(v + 8, q2[1], q2[3]);
+                                if (ch + 1 < NOUT / 16) {
+                                    q2[0] = *reinterpret_cast<const uint4*>(p.res2_hi + o + cc + 16);
+                                    q2[1] = *reinterpret_cast<const uint4*>(p.res2_hi + o + cc + 24);
+                                    q2[2] = *reinterpret_cast<const uint4*>(p.res2_lo + o + cc + 16);
+                                    q2[3] = *reinterpret_cast<const uint4*>(p.res2_lo + o + cc + 24);
+                                }
+                            }
+                            if (tma_out) store_split16_smem(orow_hi, orow_lo, cc >> 3, r7, v, p.relu);
+                            else if (ok) store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
                         }
                     }
-                    if (h0 == 0) {
-                        mbar_wait(&tfull[ab], aphase);
-                        tc_fence_after();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader);
+                    if (tma_out) {  // hand the finished tile to the store thread (warp 6)
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's tile rows -> visible to the bulk copy engine
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&outFull[sbuf]);
                     }
-#pragma unroll
-                    for (int c1 = 0; c1 < PRE; c1 += 16) {
-                        const int cc = h0 + c1;
-                        float v[16];
-                        pair_acc16<NA, STACK>(taddr, taddr2, cc, v);
+                } else {
+                    // The ResBlock residual of this pixel is fetched into registers BEFORE waiting for the accumulator (up to 128
+                    // channels at a time), so its latency hides behind the tile's MMA main loop.  tcgen05.ld is .sync.aligned:
+                    // every lane of the warp executes it, only the memory accesses depend on `ok`.
+                    // Both residuals (ResBlock input, U-skip) are summed into fp32 registers here: the last conv of an up level used to fetch
+                    // its second residual inside the drain loop, one exposed global-memory latency per 16 channels (profiles/r02u_pair_roles.md).
+                    constexpr int PRE = NOUT < 128 ? NOUT : 128;
+                    const bool has_r1 = ok && (p.res1_hi != nullptr), has_r2 = ok && (p.res2_hi != nullptr);
+                    float rs[PRE];
+    #pragma unroll
+                    for (int h0 = 0; h0 < NOUT; h0 += PRE) {
+                        if (has_r1 || has_r2) {
+    #pragma unroll
+                            for (int i = 0; i < PRE; ++i) rs[i] = 0.f;
+                        }
                         if (has_r1) {
-                            add_split8(v, rh[c1 / 8], rl[c1 / 8]);
-                            add_split8(v + 8, rh[c1 / 8 + 1], rl[c1 / 8 + 1]);
+                            const uint4* gh = reinterpret_cast<const uint4*>(p.res1_hi + o + h0);
+                            const uint4* gl = reinterpret_cast<const uint4*>(p.res1_lo + o + h0);
+    #pragma unroll
+                            for (int i = 0; i < PRE / 8; ++i) add_split8(rs + 8 * i, gh[i], gl[i]);
                         }
                         if (has_r2) {
-                            const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o + cc);
-                            const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o + cc);
-                            add_split8(v, gh[0], gl[0]);
-                            add_split8(v + 8, gh[1], gl[1]);
+                            const uint4* gh = reinterpret_cast<const uint4*>(p.res2_hi + o + h0);
+                            const uint4* gl = reinterpret_cast<const uint4*>(p.res2_lo + o + h0);
+    #pragma unroll
+                            for (int i = 0; i < PRE / 8; ++i) add_split8(rs + 8 * i, gh[i], gl[i]);
                         }
-                        if (ok) store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
+                        if (h0 == 0) {
+                            TC_PROF_T0();
+                            mbar_wait(&tfull[ab], aphase);
+                            TC_PROF_ADD(prof_w3);
+                            tc_fence_after();
+                        }
+                        if (p.dual & 32) continue;  // timing experiment: the epilogue only hands the accumulator back
+    #pragma unroll
+                        for (int c1 = 0; c1 < PRE; c1 += 16) {
+                            const int cc = h0 + c1;
+                            float v[16];
+                            pair_acc16<NA, STACK>(taddr, taddr2, cc, v, resw);
+                            if (has_r1 || has_r2) {
+    #pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += rs[c1 + j];
+                            }
+                            if (ok) store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
+                        }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(tempty_leader);
             } else {
                 mbar_wait(&tfull[ab], aphase);
                 tc_fence_after();
@@ -1048,7 +1311,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
 #pragma unroll 1
                     for (int cc = 0; cc < NOUT; cc += 16) {
                         float v[16];
-                        pair_acc16<NA, STACK>(taddr, taddr2, cc, v);
+                        pair_acc16<NA, STACK>(taddr, taddr2, cc, v, resw);
                         float4* d = reinterpret_cast<float4*>(prow + cc);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -1070,6 +1333,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     }
                 }
             }
+        }
+        if (threadIdx.x == 64) {
+            TC_PROF_PUT(4, clock64() - role_t0);
+            TC_PROF_PUT(3, prof_w3);
         }
     }
     if (lane == 0) TC_TRACE(6, 0x1000 + warp);
@@ -1294,6 +1561,9 @@ int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
     k.cluster_splitk = cluster_splitk;
     k.dual = 0;
     k.resw = 0;
+    k.tma_out = 0;
+    k.res_tma = 0;
+    k.prof = nullptr;
     if (BN == 64) {
         if (p.mode == TC_CONV3X3) return launch_tc<64, 0>(ctx, maps, k, grid);
         if (p.mode == TC_DOWN2X2) return launch_tc<64, 1>(ctx, maps, k, grid);
@@ -1362,10 +1632,23 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
     cudaLaunchConfig_t cfg = {};
     // A/B switches (tests, profiling): QMRI_TC_DUAL=1 turns the second MMA issuer on (measured 3 % slower: off by default),
     // QMRI_TC_RESW=0 turns the resident weights of the 64 -> 64 layers off
-    static const bool dual_on = getenv("QMRI_TC_DUAL") && !strcmp(getenv("QMRI_TC_DUAL"), "1");
+    static const int dual_on = getenv("QMRI_TC_DUAL") ? atoi(getenv("QMRI_TC_DUAL")) : 0;   // 1: second issuer; 4 / 8 / 12: timing experiments
     static const bool resw_off = getenv("QMRI_TC_RESW") && !strcmp(getenv("QMRI_TC_RESW"), "0");
-    k.dual = (Cfg::DUAL_OK && dual_on) ? 1 : 0;
-    k.resw = (Cfg::DUAL_OK && !resw_off && p.Cin == TC_BK) ? 1 : 0;
+    static const int resw_stages = getenv("QMRI_TC_RESW") ? atoi(getenv("QMRI_TC_RESW")) : 1;   // 2 / 3: cap on the slab stages
+    k.dual = Cfg::DUAL_OK ? (dual_on & ~1) : 0;  // (the second-issuer mode, bit 0, is retired: its epilogue is gone)
+    // QMRI_TC_DBG_LAYER=n: the experiment bits (and the profile line) apply to every 16th launch of this kernel only, starting with
+    // the n-th - one layer of a forward runs the experiment on real data while the others run normally
+    static const int dbg_layer = getenv("QMRI_TC_DBG_LAYER") ? atoi(getenv("QMRI_TC_DBG_LAYER")) : -1;
+    static int launch_no = 0;
+    bool dbg_this = true;
+    if (Cfg::DUAL_OK && dbg_layer >= 0) {
+        dbg_this = (launch_no++ % 16) == dbg_layer;
+        if (!dbg_this) k.dual = 0;
+    }
+    k.resw = (Cfg::DUAL_OK && !resw_off && p.Cin == TC_BK) ? (resw_stages >= 2 ? resw_stages : 1) : 0;
+    static const bool tma_out_off = getenv("QMRI_TC_TMAOUT") && !strcmp(getenv("QMRI_TC_TMAOUT"), "0");  // A/B switch
+    k.tma_out = (k.resw && p.mapO_hi && p.mapO_lo && !tma_out_off) ? 1 : 0;
+    k.res_tma = (k.tma_out && p.res1_hi && p.mapR_hi && p.mapR_lo) ? 1 : 0;
     cfg.gridDim = dim3(nclusters * 2);
     cfg.blockDim = dim3(PAIR_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM;
@@ -1390,9 +1673,36 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
         memset(trace_host, 0, 256 * 8 * sizeof(int));
         k.trace = trace_dev;
     }
+    // QMRI_TC_PROF=1: role-level attribution - cycles each role of each CTA spends waiting (serialises the launches)
+    static unsigned long long* prof_dev = nullptr;
+    static const bool prof_on = getenv("QMRI_TC_PROF") != nullptr;
+    k.prof = nullptr;
+    if (prof_on) {
+        if (!prof_dev) QCUDA(cudaMalloc((void**)&prof_dev, 256 * 16 * sizeof(unsigned long long)));
+        QCUDA(cudaMemsetAsync(prof_dev, 0, 256 * 16 * sizeof(unsigned long long), ctx->stream));
+        k.prof = prof_dev;
+    }
     QCUDA(cudaLaunchKernelEx(&cfg, tc_conv3x3_pair_kernel<NA, STACK>, *(const CUtensorMap*)p.mapA_hi[0], *(const CUtensorMap*)p.mapA_lo[0],
-                             *(const CUtensorMap*)p.mapB_hi, *(const CUtensorMap*)p.mapB_lo, *(const CUtensorMap*)p.mapB_h2, (const TcK)k));
+                             *(const CUtensorMap*)p.mapB_hi, *(const CUtensorMap*)p.mapB_lo, *(const CUtensorMap*)p.mapB_h2,
+                             *(const CUtensorMap*)(p.mapB_l2 ? p.mapB_l2 : p.mapB_h2),
+                             *(const CUtensorMap*)(p.mapO_hi ? p.mapO_hi : p.mapA_hi[0]), *(const CUtensorMap*)(p.mapO_lo ? p.mapO_lo : p.mapA_lo[0]),
+                             *(const CUtensorMap*)(p.mapR_hi ? p.mapR_hi : p.mapA_hi[0]), *(const CUtensorMap*)(p.mapR_lo ? p.mapR_lo : p.mapA_lo[0]),
+                             (const TcK)k));
     QLAUNCH_CHECK(ctx);
+    if (prof_on && dbg_this) {
+        std::vector<unsigned long long> h(256 * 16);
+        QCUDA(cudaStreamSynchronize(ctx->stream));
+        QCUDA(cudaMemcpy(h.data(), prof_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        double a[16] = {};
+        int nl = 0;
+        for (int c = 0; c < nclusters * 2; c += 2, ++nl)  // leader CTAs
+            for (int j = 0; j < 16; ++j) a[j] += (double)h[c * 16 + j];
+        for (int j = 0; j < 16; ++j) a[j] /= nl;
+        fprintf(stderr, "[qmri prof] pair<%d,%d> S=%d %dx%d Cin=%d Cout=%d resw=%d: per leader CTA: tiles %.1f, MMA role %.0f cycles in %.0f ns (%.0f MHz) = %.0f per tile "
+                        "(waiting for slabs %.0f, for a free accumulator %.0f; inside the MMA issue loops %.0f, inside commits %.0f), producer waiting for a free stage %.0f, epilogue role %.0f "
+                        "(waiting for the accumulator %.0f)\n",
+                NA, STACK, p.S, p.H, p.W, p.Cin, p.Cout, k.resw, a[7], a[2], a[6], a[6] > 0 ? 1e3 * a[2] / a[6] : 0.0, a[2] / (a[7] > 0 ? a[7] : 1), a[0], a[1], a[8], a[9], a[5], a[4], a[3]);
+    }
     if (trace_on) {  // watchdog: a hang dumps where every role of every CTA stopped, then the process exits
         for (int ms = 0; ms < 5000; ++ms) {
             if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady) return QMRI_OK;
@@ -1699,7 +2009,7 @@ int conv3x3_tc_pair(qmri_ctx* ctx, const TcConvParams& p) {
     k.partial = p.partial; k.tickets = p.tickets;
     k.S = p.S; k.H = p.H; k.W = p.W; k.Cin = p.Cin; k.Cout = p.Cout;
     k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
-    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr; k.cluster_splitk = 0; k.dual = 0; k.resw = 0;
+    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr; k.cluster_splitk = 0; k.dual = 0; k.resw = 0; k.tma_out = 0; k.res_tma = 0; k.prof = nullptr;
     if (p.Cout == 64) return launch_pair<128, 1>(ctx, p, k);
     if (p.Cout == 128) return launch_pair<256, 1>(ctx, p, k);
     return launch_pair<256, 0>(ctx, p, k);

@@ -167,6 +167,7 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
         net->wmapp_hi[o].resize(64);
         net->wmapp_lo[o].resize(64);
         net->wmapp_h2[o].resize(64);
+        net->wmapp_l2[o].resize(64);
         std::vector<uint16_t> hi, lo;
         for (int l = 0; l < 64 && net->tc_available; ++l) {
             if (L[l].kind > 2) continue;
@@ -188,7 +189,8 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
                 tc_pair_weight_boxes(L[l].cout, &rows_main, &rows_h2);
                 r = tc_make_weight_map(&net->wmapp_hi[o][l], net->wtc_hi[o][l], K, N, rows_main) |
                     tc_make_weight_map(&net->wmapp_lo[o][l], net->wtc_lo[o][l], K, N, rows_main) |
-                    tc_make_weight_map(&net->wmapp_h2[o][l], net->wtc_hi[o][l], K, N, rows_h2);
+                    tc_make_weight_map(&net->wmapp_h2[o][l], net->wtc_hi[o][l], K, N, rows_h2) |
+                    tc_make_weight_map(&net->wmapp_l2[o][l], net->wtc_lo[o][l], K, N, rows_h2);
             }
             if (r) net->tc_available = false;  // driver entry point missing: tensor mode off, exact fp32 mode still works
         }
@@ -351,6 +353,10 @@ static int build_act_maps(qmri_net* net, int H, int W) {
             tc_slab_tile_shape(W >> l, H >> l, &SW, &SH);
             QCHECK(tc_make_act_map(&net->amap_slab[b][l][0], hi[b][l], net->chunk, H >> l, W >> l, NC[l], SW, SH + 2));
             QCHECK(tc_make_act_map(&net->amap_slab[b][l][1], lo[b][l], net->chunk, H >> l, W >> l, NC[l], SW, SH + 2));
+            if (l == 0) {
+                QCHECK(tc_make_act_map(&net->amap_tile[b][0], hi[b][0], net->chunk, H, W, NC[0], SW, SH));
+                QCHECK(tc_make_act_map(&net->amap_tile[b][1], lo[b][0], net->chunk, H, W, NC[0], SW, SH));
+            }
             if (l == 0 && conv64_swap_supported(W, H, NC[0], NC[0])) {
                 QCHECK(tc_make_act_map(&net->amap_swap[b][0], hi[b][0], net->chunk, H, W, NC[0], 16, 16));
                 QCHECK(tc_make_act_map(&net->amap_swap[b][1], lo[b][0], net->chunk, H, W, NC[0], 16, 16));
@@ -464,6 +470,13 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
             p.mapA_hi[0] = &net->amap_slab[src][lvl][0]; p.mapA_lo[0] = &net->amap_slab[src][lvl][1];
             p.mapB_hi = &net->wmapp_hi[orient][layer]; p.mapB_lo = &net->wmapp_lo[orient][layer];
             p.mapB_h2 = &net->wmapp_h2[orient][layer];
+            p.mapB_l2 = &net->wmapp_l2[orient][layer];
+            if (lvl == 0) {
+                p.mapO_hi = &net->amap_tile[dst][0]; p.mapO_lo = &net->amap_tile[dst][1];
+                if (r1 >= 0) {
+                    p.mapR_hi = &net->amap_tile[r1][0]; p.mapR_lo = &net->amap_tile[r1][1];
+                }
+            }
             return conv3x3_tc_pair(ctx, p);
         }
         p.mapA_hi[0] = &net->amap[src][lvl][0]; p.mapA_lo[0] = &net->amap[src][lvl][1];

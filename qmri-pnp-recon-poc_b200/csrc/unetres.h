@@ -32,9 +32,10 @@ struct qmri_net {
     // activation TMA maps per workspace buffer (X, A, T) x level x plane (hi, lo); rebuilt when the workspace moves
     TMap amap[3][4][2];
     TMap amap_slab[3][4][2];     // (BH + 2) x BW slabs for the CTA-pair 3x3 kernel
+    TMap amap_tile[3][2];        // level 0: BH x BW tiles of the CTA-pair kernel (output side: bulk tensor stores of the 64 -> 64 layers)
     TMap amap_swap[3][2];        // level 0: (14 + 2) x 16 slabs for the operand-swapped 64 -> 64 kernel (conv64_swap)
     int tc_swap = 0;             // 1 = the 64 -> 64 convs of level 0 run through conv64_swap when the batch fills the machine (QMRI_TC_SWAP)
-    std::vector<TMap> wmapp_hi[2], wmapp_lo[2], wmapp_h2[2];  // 3x3 weights with the box rows of the CTA-pair kernel
+    std::vector<TMap> wmapp_hi[2], wmapp_lo[2], wmapp_h2[2], wmapp_l2[2];  // 3x3 weights with the box rows of the CTA-pair kernel
     int tc_pair = 15;            // 3x3 convs, bit l = level l: 1 = CTA-pair kernel (cta_group::2, slab A reuse), 0 = single-CTA per-tap kernel
     TMap amap_down[3][3][4][2];  // buffer x input level x tap (dy*2+dx) x plane: stride-2 views for the 2x2 s2 convs
     float* tc_partial = nullptr; // split-K workspace and tickets (conv_tc.cu)
