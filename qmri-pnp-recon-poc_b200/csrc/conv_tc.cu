@@ -150,6 +150,25 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1)
+// warp-converged forms (whole warp executes, one elected lane issues): see tc2_mma_elect below for why
+__device__ __forceinline__ void tc_mma_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     const uint64_t lo = (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16);
     const uint64_t hi = (uint64_t)64 | ((uint64_t)1 << 14) | ((uint64_t)2 << 29);
@@ -464,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shuffle: tells ptxas the warp index is warp-uniform
     const int cblocks = p.Cin / TC_BK;
     const int KB = TAPS * cblocks;
     const int NT = ((MODE == 2) ? 4 * p.Cout : p.Cout) / BN;
@@ -494,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_wait();  // everything below reads activations / partials / tickets produced by earlier kernels
     size_t cs_o = 0;      // cluster split-K: this thread's output offset / validity / tile row (epilogue warps)
     bool cs_ok = false;
@@ -539,8 +558,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (the whole warp runs the loop, one elected lane issues: see tc2_mma_elect) =================
+        {
             // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0;
@@ -563,17 +582,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes along K inside the swizzle atom (16-byte units)
-                        tc_mma(tmem_d, a_hi + ko, b_hi + ko, idesc, ((kb - kb0) | k) ? 1u : 0u);
-                        tc_mma(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
-                        tc_mma(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
+                        tc_mma_elect(tmem_d, a_hi + ko, b_hi + ko, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                        tc_mma_elect(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
+                        tc_mma_elect(tmem_d, a_lo + ko, b_hi + ko, idesc, 1u);
                     }
-                    tc_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    tc_commit_elect(&empty[stage]);  // frees the smem slot once these MMAs have read it
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(&tfull[ab]);  // accumulator complete
+                tc_commit_elect(&tfull[ab]);  // accumulator complete
             }
         }
     } else {

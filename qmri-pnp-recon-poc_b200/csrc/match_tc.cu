@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) match_tc_kernel(const __grid_
     uint64_t* tempty = a_full + 4;                   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 6);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shuffle: warp-uniform for ptxas
     const int total_work = p.ptiles * p.nsplit;
 
     // Two MMA-issuing warps for complex pixels: one thread gets a tcgen05.mma out every ~103 cycles at best (profiles/r02_tmem_a_bench.txt),
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) match_tc_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) match_tc_kernel(const __grid_
     } else if (warp == 1 || warp == 2 + EW) {
         // ================= MMA issuer(s): warp 1 (real part; both parts with a single issuer), warp 2 + EW (imaginary part) =================
         const bool second = warp != 1;
-        if (lane == 0 && (!second || two)) {
+        if (!second || two) {  // the whole warp runs the issue loop, one elected lane issues (tc_ptx.cuh)
             const bool do_re = !second, do_im = CPLX && (second || !two);
             // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MT_BN >> 3) << 17) | ((uint32_t)(MT_BM >> 4) << 24);
@@ -190,36 +190,37 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) match_tc_kernel(const __grid_
                 aphase ^= 1;
                 tc_fence_after();
                 for (int t = t0; t < t1; ++t, ++it) {
-                    const int ab = it & 1;
+                    // (the shuffles mark the loop-carried values as warp-uniform for ptxas: operands stay in uniform registers)
+                    const int ab = __shfl_sync(0xffffffffu, it & 1, 0);
                     mbar_wait(&tempty[ab], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator pair
                     mbar_wait(&b_full[stage], phase);
                     tc_fence_after();
-                    const uint64_t b = umma_desc_sw128(smem_u32(smB + (size_t)stage * MT_B_TILE));
+                    const uint64_t b = umma_desc_sw128(__shfl_sync(0xffffffffu, smem_u32(smB + (size_t)stage * MT_B_TILE), 0));
                     const uint32_t d_re = tmem_base + (uint32_t)(ab * 2 * MT_BN), d_im = d_re + MT_BN;
                     if (p.debug != 2) {
                         if (do_re) {
 #pragma unroll
                             for (int k = 0; k < MT_KF / 8; ++k) {
                                 const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes along K inside the swizzle row (16-byte units)
-                                mma_tf32_ss(d_re, a_re + ko, b + ko, idesc, k ? 1u : 0u);
+                                mma_tf32_ss_elect(d_re, a_re + ko, b + ko, idesc, k ? 1u : 0u);
                             }
                         }
                         if (do_im) {
 #pragma unroll
                             for (int k = 0; k < MT_KF / 8; ++k) {
                                 const uint64_t ko = (uint64_t)(k * 2);
-                                mma_tf32_ss(d_im, a_im + ko, b + ko, idesc, k ? 1u : 0u);
+                                mma_tf32_ss_elect(d_im, a_im + ko, b + ko, idesc, k ? 1u : 0u);
                             }
                         }
                     }
-                    tc_commit(&b_empty[stage]);
-                    tc_commit(&tfull[ab]);
+                    tc_commit_elect(&b_empty[stage]);
+                    tc_commit_elect(&tfull[ab]);
                     if (++stage == MT_STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(a_empty);  // the pixel tile may be overwritten once every MMA above has completed
+                tc_commit_elect(a_empty);  // the pixel tile may be overwritten once every MMA above has completed
             }
         }
     } else {
