@@ -204,6 +204,7 @@ struct TcK {
     int dual;            // CTA-pair kernel, Cout = 64: a second warp issues the a_lo w_hi MMAs into their own accumulator columns
     int resw;            // CTA-pair kernel, Cin = Cout = 64: the layer's weights stay resident in shared memory
     int tma_out;         // CTA-pair kernel, resw layers: the output tile leaves through shared memory + bulk tensor stores
+    int l2pf;            // CTA-pair kernel: the producer prefetches the next work item's slabs into L2
     int res_tma;         // ... and the ResBlock residual tile arrives in the same staging tile through a bulk tensor load
     unsigned long long* prof;  // QMRI_TC_PROF: per-CTA cycle counters of the pair kernel's roles (8 per CTA), else null
 };
@@ -703,7 +704,9 @@ struct PairCfg {
     static constexpr int AS = (NA == 128) ? 3 : 2;
     static constexpr int ASB = 4;                                // slab-stage barrier slots (resident-weight mode runs up to four stages)
     static constexpr int BS = (NA == 128) ? 8 : (STACK ? 5 : 4);
-    static constexpr bool DUAL_OK = STACK && NA == 128;          // room in TMEM for a separate accumulator of the a_lo w_hi product
+    static constexpr bool DUAL_OK = STACK && NA == 128;          // the 64 -> 64 instance (lean epilogue, staging tile, store thread)
+    static constexpr int EPW = DUAL_OK ? 8 : 4;                  // epilogue warps: 2 .. 5 (+ 7 .. 10: the second 32 channels of each lane quarter)
+    static constexpr int THREADS = DUAL_OK ? 352 : PAIR_THREADS;
     static constexpr uint32_t TMEM_COLS = DUAL_OK ? 512 : 2 * NA; // two accumulators (+ 2 x NA/2 columns for the second issuer's)
     static constexpr uint32_t RESW_BYTES = 9 * B1_BYTES;         // resident-weight mode: nine taps of this CTA's 64 stacked weight rows
     static constexpr size_t STAGE_AREA = (size_t)AS * A_SLOT + (size_t)BS * B_STAGE;
@@ -730,6 +733,10 @@ __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* tm, u
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
+}
+// bring a tile into L2 ahead of its shared-memory load (no shared memory, no barrier: pipeline depth that costs nothing on chip)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tc2_commit(uint64_t* bar) {  // arrive on `bar` in BOTH CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
@@ -795,7 +802,7 @@ __device__ __forceinline__ void pair_acc16(uint32_t taddr, uint32_t taddr2, int 
 }
 
 template <int NA, int STACK>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
+__global__ void __launch_bounds__(PairCfg<NA, STACK>::THREADS, 1)
 tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                        const __grid_constant__ CUtensorMap tmB_h2, const __grid_constant__ CUtensorMap tmB_l2,
@@ -853,7 +860,8 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const bool tma_out = resw && p.tma_out;
     const bool res_tma = tma_out && p.res_tma;
     constexpr uint32_t OUT_BYTES = 2 * TC_BM * 128;
-    const int as_fit = (int)((Cfg::STAGE_AREA - Cfg::RESW_BYTES - (tma_out ? 2 * OUT_BYTES : 0u)) / (2 * slab_bytes));
+    const int obufs = p.tma_out == 1 ? 1 : 2;   // staging buffers: one leaves room for a third slab stage (host's choice per layer)
+    const int as_fit = (int)((Cfg::STAGE_AREA - Cfg::RESW_BYTES - (tma_out ? obufs * OUT_BYTES : 0u)) / (2 * slab_bytes));
     uint64_t* fullR = fullB + 2;   // [2]; resw mode uses fullB[0] only, so the weight-ring barriers (count 1) are free
     uint64_t* emptyR = fullB + 4;  // [2]
     uint64_t* outFull = fullB + 6; // [2], count 4: the epilogue warps have written the finished tile into the staging buffer
@@ -861,7 +869,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const int AS_EFF = resw ? (as_fit < as_cap ? as_fit : as_cap) : AS;
     unsigned char* smemW = smem;                                      // resw: nine taps x 64 rows x 128 B
     unsigned char* smemO = smem + Cfg::RESW_BYTES;                    // tma_out: two staging tiles, each hi plane then lo plane
-    unsigned char* smemA = resw ? smem + Cfg::RESW_BYTES + (tma_out ? 2 * OUT_BYTES : 0u) : smem;      // slab stages
+    unsigned char* smemA = resw ? smem + Cfg::RESW_BYTES + (tma_out ? obufs * OUT_BYTES : 0u) : smem;      // slab stages
 
     if (threadIdx.x == 0) {
         const uint32_t nissue = dual ? 2u : 1u;  // MMA issuers that commit on the stage / accumulator barriers
@@ -875,8 +883,8 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], nissue);
-            mbar_init(&tempty[a], 8);  // 4 epilogue warps of each CTA
-            if (tma_out) mbar_init(&outFull[a], 4);
+            mbar_init(&tempty[a], 2 * Cfg::EPW);  // the epilogue warps of both CTAs
+            if (tma_out) mbar_init(&outFull[a], Cfg::EPW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmA_hi);
@@ -910,7 +918,6 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             unsigned long long prof_w5 = 0;
-            int itp = 0;
             if (resw && cidx < total_work) {  // the layer's weights, once: completion on the leader's fullB[0]
                 if (crank == 0) mbar_expect_tx(&fullB[0], 2 * Cfg::RESW_BYTES);
                 const uint32_t barW = mapa_rank(smem_u32(&fullB[0]), 0);
@@ -930,6 +937,21 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 const int s = (pt < ptiles) ? pt / tiles_xy : p.S;
                 const int x0 = (txy % p.tiles_x) * p.BW, y0 = (txy / p.tiles_x) * p.BH;
                 const int u0 = (split * U) / p.nsplit, u1 = ((split + 1) * U) / p.nsplit;
+                if (p.l2pf && w + nclusters < total_work) {  // the NEXT work item's slabs into L2 (the layer input streams from DRAM)
+                    const int w2 = w + nclusters;
+                    const int r2 = w2 / p.nsplit, split2 = w2 % p.nsplit;
+                    const int pt2 = (r2 / NT) * 2 + crank;
+                    if (pt2 < ptiles) {
+                        const int txy2 = pt2 % tiles_xy, s2 = pt2 / tiles_xy;
+                        const int px0 = (txy2 % p.tiles_x) * p.BW, py0 = (txy2 / p.tiles_x) * p.BH;
+                        const int v0 = (split2 * U) / p.nsplit, v1 = ((split2 + 1) * U) / p.nsplit;
+                        for (int u = v0; u < v1; ++u) {
+                            const int cb = u / 3, dxi = u - 3 * cb;
+                            tma_prefetch_l2_4d(&tmA_hi, cb * TC_BK, px0 + dxi - 1, py0 - 1, s2);
+                            tma_prefetch_l2_4d(&tmA_lo, cb * TC_BK, px0 + dxi - 1, py0 - 1, s2);
+                        }
+                    }
+                }
                 for (int u = u0; u < u1; ++u) {
                     const int cb = u / 3, dxi = u - 3 * cb;
                     TC_TRACE(0, (w << 12) | (u << 4) | 1);
@@ -972,15 +994,6 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         }
                     }
                 }
-                if (res_tma) {  // after the tile's slabs: this CTA's residual tile into staging buffer itp & 1, once its previous bulk store has been read out
-                    const int rb = itp & 1;
-                    mbar_wait(&emptyR[rb], ((uint32_t)(itp >> 1) & 1u) ^ 1u);
-                    mbar_expect_tx(&fullR[rb], OUT_BYTES);
-                    unsigned char* rp = smemO + (size_t)rb * OUT_BYTES;
-                    tma_load_4d(rp, &tmR_hi, &fullR[rb], 0, x0, y0, s);
-                    tma_load_4d(rp + TC_BM * 128, &tmR_lo, &fullR[rb], 0, x0, y0, s);
-                }
-                ++itp;
             }
             TC_PROF_PUT(5, prof_w5);
         }
@@ -1094,12 +1107,26 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     } else if (warp == 6) {
         // ================= store thread (64 -> 64 layers): finished tiles leave through bulk tensor stores =================
         if (lane == 0 && tma_out) {
+            // residual tile of work item w2 into staging buffer b (bulk tensor load; the epilogue warps wait on fullR[b]).  Issued by
+            // THIS thread because it knows when a buffer's previous store has been read out - a whole tile time before the
+            // epilogue needs the residual - and the slab producer never waits for a staging buffer.
+            auto load_residual = [&](int w2, int b) {
+                if (!res_tma || w2 >= total_work) return;
+                const int pt2 = ((w2 / p.nsplit) / NT) * 2 + crank;
+                const int txy2 = pt2 % tiles_xy, s2 = (pt2 < ptiles) ? pt2 / tiles_xy : p.S;  // past the last tile: all out of bounds (zeros)
+                const int rx0 = (txy2 % p.tiles_x) * p.BW, ry0 = (txy2 / p.tiles_x) * p.BH;
+                mbar_expect_tx(&fullR[b], OUT_BYTES);
+                unsigned char* rp = smemO + (size_t)b * OUT_BYTES;
+                tma_load_4d(rp, &tmR_hi, &fullR[b], 0, rx0, ry0, s2);
+                tma_load_4d(rp + TC_BM * 128, &tmR_lo, &fullR[b], 0, rx0, ry0, s2);
+            };
+            for (int b = 0; b < obufs; ++b) load_residual(cidx + b * nclusters, b);
             int it = 0;
             for (int w = cidx; w < total_work; w += nclusters, ++it) {
                 const int pt = ((w / p.nsplit) / NT) * 2 + crank;
                 const int txy = pt % tiles_xy, s = pt / tiles_xy;
-                const int sbuf = it & 1;
-                mbar_wait(&outFull[sbuf], (uint32_t)(it >> 1) & 1u);
+                const int sbuf = obufs == 2 ? (it & 1) : 0;
+                mbar_wait(&outFull[sbuf], (uint32_t)(obufs == 2 ? it >> 1 : it) & 1u);
                 if (pt < ptiles && !(p.dual & 32)) {
                     const int tx0 = (txy % p.tiles_x) * p.BW, ty0 = (txy / p.tiles_x) * p.BH;
                     tma_store_4d(&tmO_hi, smem_u32(smemO) + (uint32_t)sbuf * OUT_BYTES, 0, tx0, ty0, s);
@@ -1107,7 +1134,8 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer has been read out: hand it back
-                mbar_arrive(&emptyR[sbuf]);
+                if (res_tma) load_residual(w + obufs * nclusters, sbuf);   // ... to the residual tile of its next user
+                else mbar_arrive(&emptyR[sbuf]);                          // ... or straight to the epilogue warps
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every bulk store of this CTA has completed
         }
@@ -1170,7 +1198,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         const int row = lg * 32 + lane;
         int it = 0;
         const long long role_t0 = p.prof ? clock64() : 0;
-        unsigned long long prof_w3 = 0;
+        unsigned long long prof_w3 = 0, prof_w10 = 0, prof_w11 = 0, prof_w12 = 0, prof_w13 = 0;
         for (int w = cidx; w < total_work; w += nclusters, ++it) {
             const int split = w % p.nsplit;
             const int r = w / p.nsplit;
@@ -1195,21 +1223,24 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     // next chunk in flight; the ResBlock residual comes from the staging tile (filled by the producer's bulk tensor
                     // load), the result goes back into the same row of that tile and leaves with two bulk tensor stores.  Without the
                     // tile maps (tma_out off) residuals and outputs use 16-byte global accesses (slow, kept for A/B runs).
-                    const int sbuf = it & 1;
-                    const uint32_t suse = (uint32_t)(it >> 1);
+                    const int sbuf = obufs == 2 ? (it & 1) : 0;
+                    const uint32_t suse = (uint32_t)(obufs == 2 ? it >> 1 : it);
                     const uint32_t orow_hi = smem_u32(smemO) + (uint32_t)sbuf * OUT_BYTES + (uint32_t)row * 128u, orow_lo = orow_hi + TC_BM * 128u;
                     const int r7 = row & 7;
                     const bool g_r1 = ok && !res_tma && (p.res1_hi != nullptr), g_r2 = ok && (p.res2_hi != nullptr);
                     uint4 q2[4];  // second residual (U-skip; last conv of a level only): global, fetched one chunk ahead
                     if (g_r2) {
-                        q2[0] = *reinterpret_cast<const uint4*>(p.res2_hi + o);
-                        q2[1] = *reinterpret_cast<const uint4*>(p.res2_hi + o + 8);
-                        q2[2] = *reinterpret_cast<const uint4*>(p.res2_lo + o);
-                        q2[3] = *reinterpret_cast<const uint4*>(p.res2_lo + o + 8);
+                        const int c0 = (Cfg::EPW == 8 && warp >= 7) ? NOUT / 2 : 0;
+                        q2[0] = *reinterpret_cast<const uint4*>(p.res2_hi + o + c0);
+                        q2[1] = *reinterpret_cast<const uint4*>(p.res2_hi + o + c0 + 8);
+                        q2[2] = *reinterpret_cast<const uint4*>(p.res2_lo + o + c0);
+                        q2[3] = *reinterpret_cast<const uint4*>(p.res2_lo + o + c0 + 8);
                     }
                     if (tma_out) {  // staging buffer: residual tile landed / previous bulk store of this buffer read out
+                        TC_PROF_T0();
                         if (res_tma) mbar_wait(&fullR[sbuf], suse & 1u);
                         else mbar_wait(&emptyR[sbuf], (suse & 1u) ^ 1u);
+                        TC_PROF_ADD(prof_w11);
                     }
                     {
                         TC_PROF_T0();
@@ -1217,15 +1248,28 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         TC_PROF_ADD(prof_w3);
                     }
                     tc_fence_after();
+                    const long long drain_t0 = p.prof ? clock64() : 0;
                     if (!(p.dual & 32)) {  // (QMRI_TC_DUAL=32, timing experiment: the epilogue only hands the accumulator back)
+                        // eight epilogue warps: warps 2 - 5 take channels [0, 32) of their lane quarter, warps 7 - 10 channels [32, 64)
+                        // (one warp per scheduler cannot hide its own ALU / LDTM latencies: ~5 cycles per instruction were measured)
+                        constexpr int CPW = NOUT / 16 / (Cfg::EPW / 4);   // 16-channel chunks per warp
+                        const int ch0 = (Cfg::EPW == 8 && warp >= 7) ? CPW : 0;
                         uint32_t ta[2][16], tb[2][16];
-                        tc_ld16(taddr, ta[0]);
-                        tc_ld16(taddr + (resw ? 3 * NA / 4 : NA / 2), tb[0]);
+                        {
+                            const int c0 = 16 * ch0;
+                            tc_ld16(taddr + c0, ta[0]);
+                            tc_ld16(taddr + (resw ? (c0 < NA / 4 ? 3 * NA / 4 : NA / 4) : NA / 2) + c0, tb[0]);
+                        }
 #pragma unroll
-                        for (int ch = 0; ch < NOUT / 16; ++ch) {
-                            const int cc = 16 * ch, cur = ch & 1;
-                            tc_wait_ld();
-                            if (ch + 1 < NOUT / 16) {  // second term of channel c: column c + 96 (c < 32) or c + 32 (c >= 32), see pair_acc16
+                        for (int ci = 0; ci < CPW; ++ci) {
+                            const int ch = ch0 + ci;
+                            const int cc = 16 * ch, cur = ci & 1;
+                            {
+                                TC_PROF_T0();
+                                tc_wait_ld();
+                                TC_PROF_ADD(prof_w10);
+                            }
+                            if (ci + 1 < CPW) {  // second term of channel c: column c + 96 (c < 32) or c + 32 (c >= 32), see pair_acc16
                                 const int cn = cc + 16;
                                 tc_ld16(taddr + cn, ta[cur ^ 1]);
                                 tc_ld16(taddr + (resw ? (cn < NA / 4 ? 3 * NA / 4 : NA / 4) : NA / 2) + cn, tb[cur ^ 1]);
@@ -1251,7 +1295,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             if (g_r2) {
                                 add_split8(v, q2[0], q2[2]);
                                 add_split8(v + 8, q2[1], q2[3]);
-                                if (ch + 1 < NOUT / 16) {
+                                if (ci + 1 < CPW) {
                                     q2[0] = *reinterpret_cast<const uint4*>(p.res2_hi + o + cc + 16);
                                     q2[1] = *reinterpret_cast<const uint4*>(p.res2_hi + o + cc + 24);
                                     q2[2] = *reinterpret_cast<const uint4*>(p.res2_lo + o + cc + 16);
@@ -1262,6 +1306,8 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             else if (ok) store_split16(p.out_hi + o + cc, p.out_lo + o + cc, v, p.relu);
                         }
                     }
+                    if (p.prof) prof_w12 += (unsigned long long)(clock64() - drain_t0);
+                    const long long post_t0 = p.prof ? clock64() : 0;
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(tempty_leader);
@@ -1270,6 +1316,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&outFull[sbuf]);
                     }
+                    if (p.prof) prof_w13 += (unsigned long long)(clock64() - post_t0);
                 } else {
                     // The ResBlock residual of this pixel is fetched into registers BEFORE waiting for the accumulator (up to 128
                     // channels at a time), so its latency hides behind the tile's MMA main loop.  tcgen05.ld is .sync.aligned:
@@ -1356,6 +1403,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         if (threadIdx.x == 64) {
             TC_PROF_PUT(4, clock64() - role_t0);
             TC_PROF_PUT(3, prof_w3);
+            TC_PROF_PUT(10, prof_w10);
+            TC_PROF_PUT(11, prof_w11);
+            TC_PROF_PUT(12, prof_w12);
+            TC_PROF_PUT(13, prof_w13);
         }
     }
     if (lane == 0) TC_TRACE(6, 0x1000 + warp);
@@ -1582,6 +1633,7 @@ int conv_tc(qmri_ctx* ctx, const TcConvParams& p) {
     k.resw = 0;
     k.tma_out = 0;
     k.res_tma = 0;
+    k.l2pf = 0;
     k.prof = nullptr;
     if (BN == 64) {
         if (p.mode == TC_CONV3X3) return launch_tc<64, 0>(ctx, maps, k, grid);
@@ -1666,10 +1718,14 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
     }
     k.resw = (Cfg::DUAL_OK && !resw_off && p.Cin == TC_BK) ? (resw_stages >= 2 ? resw_stages : 1) : 0;
     static const bool tma_out_off = getenv("QMRI_TC_TMAOUT") && !strcmp(getenv("QMRI_TC_TMAOUT"), "0");  // A/B switch
-    k.tma_out = (k.resw && p.mapO_hi && p.mapO_lo && !tma_out_off) ? 1 : 0;
+    // tma_out: 2 = two staging buffers + two slab stages, 1 = one staging buffer + three slab stages (QMRI_TC_OUTBUF=1 / 2 forces one)
+    static const int outbuf_env = getenv("QMRI_TC_OUTBUF") ? atoi(getenv("QMRI_TC_OUTBUF")) : 0;
+    k.tma_out = (k.resw && p.mapO_hi && p.mapO_lo && !tma_out_off) ? (outbuf_env == 1 || outbuf_env == 2 ? outbuf_env : (p.res1_hi ? 2 : 1)) : 0;
     k.res_tma = (k.tma_out && p.res1_hi && p.mapR_hi && p.mapR_lo) ? 1 : 0;
+    static const int l2pf_env = getenv("QMRI_TC_L2PF") ? atoi(getenv("QMRI_TC_L2PF")) : 0;   // A/B switch: 1 = on for all pair layers
+    k.l2pf = l2pf_env > 0 ? 1 : 0;   // measured: no gain (the slab stream is throughput-, not latency-bound), off by default
     cfg.gridDim = dim3(nclusters * 2);
-    cfg.blockDim = dim3(PAIR_THREADS);
+    cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[2];
@@ -1719,8 +1775,8 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
         for (int j = 0; j < 16; ++j) a[j] /= nl;
         fprintf(stderr, "[qmri prof] pair<%d,%d> S=%d %dx%d Cin=%d Cout=%d resw=%d: per leader CTA: tiles %.1f, MMA role %.0f cycles in %.0f ns (%.0f MHz) = %.0f per tile "
                         "(waiting for slabs %.0f, for a free accumulator %.0f; inside the MMA issue loops %.0f, inside commits %.0f), producer waiting for a free stage %.0f, epilogue role %.0f "
-                        "(waiting for the accumulator %.0f)\n",
-                NA, STACK, p.S, p.H, p.W, p.Cin, p.Cout, k.resw, a[7], a[2], a[6], a[6] > 0 ? 1e3 * a[2] / a[6] : 0.0, a[2] / (a[7] > 0 ? a[7] : 1), a[0], a[1], a[8], a[9], a[5], a[4], a[3]);
+                        "(waiting for the accumulator %.0f, for the staging buffer %.0f, inside tcgen05.wait::ld %.0f, drain loop %.0f, fences + hand-over %.0f)\n",
+                NA, STACK, p.S, p.H, p.W, p.Cin, p.Cout, k.resw, a[7], a[2], a[6], a[6] > 0 ? 1e3 * a[2] / a[6] : 0.0, a[2] / (a[7] > 0 ? a[7] : 1), a[0], a[1], a[8], a[9], a[5], a[4], a[3], a[11], a[10], a[12], a[13]);
     }
     if (trace_on) {  // watchdog: a hang dumps where every role of every CTA stopped, then the process exits
         for (int ms = 0; ms < 5000; ++ms) {
@@ -2028,7 +2084,7 @@ int conv3x3_tc_pair(qmri_ctx* ctx, const TcConvParams& p) {
     k.partial = p.partial; k.tickets = p.tickets;
     k.S = p.S; k.H = p.H; k.W = p.W; k.Cin = p.Cin; k.Cout = p.Cout;
     k.BW = p.BW; k.BH = p.BH; k.tiles_x = p.tiles_x; k.tiles_y = p.tiles_y;
-    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr; k.cluster_splitk = 0; k.dual = 0; k.resw = 0; k.tma_out = 0; k.res_tma = 0; k.prof = nullptr;
+    k.relu = p.relu; k.nsplit = 1; k.trace = nullptr; k.cluster_splitk = 0; k.dual = 0; k.resw = 0; k.tma_out = 0; k.res_tma = 0; k.l2pf = 0; k.prof = nullptr;
     if (p.Cout == 64) return launch_pair<128, 1>(ctx, p, k);
     if (p.Cout == 128) return launch_pair<256, 1>(ctx, p, k);
     return launch_pair<256, 0>(ctx, p, k);
