@@ -721,6 +721,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// accumulator hand-back: nothing this thread WROTE has to become visible with the arrival (the TMEM reads are ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync), so the arrival is relaxed - the release form cost ~1000 cycles per tile
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA tile loads of a CTA pair: data lands in this CTA, completion is signalled on `bar_cluster_addr` (the leader's barrier)
 __device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -1307,10 +1312,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         }
                     }
                     if (p.prof) prof_w12 += (unsigned long long)(clock64() - drain_t0);
-                    const long long post_t0 = p.prof ? clock64() : 0;
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty_leader);
+                    if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader);
+                    const long long post_t0 = p.prof ? clock64() : 0;
                     if (tma_out) {  // hand the finished tile to the store thread (warp 6)
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's tile rows -> visible to the bulk copy engine
                         __syncwarp();
@@ -1775,7 +1780,7 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
         for (int j = 0; j < 16; ++j) a[j] /= nl;
         fprintf(stderr, "[qmri prof] pair<%d,%d> S=%d %dx%d Cin=%d Cout=%d resw=%d: per leader CTA: tiles %.1f, MMA role %.0f cycles in %.0f ns (%.0f MHz) = %.0f per tile "
                         "(waiting for slabs %.0f, for a free accumulator %.0f; inside the MMA issue loops %.0f, inside commits %.0f), producer waiting for a free stage %.0f, epilogue role %.0f "
-                        "(waiting for the accumulator %.0f, for the staging buffer %.0f, inside tcgen05.wait::ld %.0f, drain loop %.0f, fences + hand-over %.0f)\n",
+                        "(waiting for the accumulator %.0f, for the staging buffer %.0f, inside tcgen05.wait::ld %.0f, drain loop + accumulator hand-back %.0f, proxy fence + tile hand-over %.0f)\n",
                 NA, STACK, p.S, p.H, p.W, p.Cin, p.Cout, k.resw, a[7], a[2], a[6], a[6] > 0 ? 1e3 * a[2] / a[6] : 0.0, a[2] / (a[7] > 0 ? a[7] : 1), a[0], a[1], a[8], a[9], a[5], a[4], a[3], a[11], a[10], a[12], a[13]);
     }
     if (trace_on) {  // watchdog: a hang dumps where every role of every CTA stopped, then the process exits
