@@ -252,6 +252,18 @@ __global__ void __launch_bounds__(256) resample_gemm_fp32_kernel(ConvParams p) {
 constexpr int HT_TW = 32, HT_PITCH = 36;   // tile width; patch row pitch in floats (34 used; 36 keeps rows 16-byte aligned)
 constexpr int HEAD_WPITCH = 80;            // weights [9][Cin][4 cb][20]: 20-float blocks put the four cb lanes on different banks
 // TH = tile height (8, or 4 for one or two slices: twice the CTAs for 148 SMs); CTA = 32 TH threads.
+// (d0, d1) += a * (b0, b1) as ONE packed FP32 instruction (FFMA2, sm_100): same rounding as two fmaf, half the issue slots
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %2};\n\t"
+        "mov.b64 rb, {%3, %4};\n\t"
+        "mov.b64 rd, {%0, %1};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rd;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a), "f"(b0), "f"(b1));
+}
+
 template <int TH>
 __global__ void __launch_bounds__(32 * TH, (TH == 8 ? 3 : 1)) head_fp32_kernel(HeadTailParams p) {
     constexpr int HEAD_TH = TH, HEAD_ROWS = TH + 2, NT = 32 * TH;
@@ -323,10 +335,8 @@ __global__ void __launch_bounds__(32 * TH, (TH == 8 ? 3 : 1)) head_fp32_kernel(H
                     const float4 b = wp[q];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        acc[i][4 * q + 0] = fmaf(a[i + sx], b.x, acc[i][4 * q + 0]);
-                        acc[i][4 * q + 1] = fmaf(a[i + sx], b.y, acc[i][4 * q + 1]);
-                        acc[i][4 * q + 2] = fmaf(a[i + sx], b.z, acc[i][4 * q + 2]);
-                        acc[i][4 * q + 3] = fmaf(a[i + sx], b.w, acc[i][4 * q + 3]);
+                        ffma2(acc[i][4 * q + 0], acc[i][4 * q + 1], a[i + sx], b.x, b.y);
+                        ffma2(acc[i][4 * q + 2], acc[i][4 * q + 3], a[i + sx], b.z, b.w);
                     }
                 }
             }
@@ -411,11 +421,11 @@ __global__ void __launch_bounds__(32 * TH, (TH == 8 ? 4 : 1)) tail_fp32_kernel(H
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float av = a[i + sx];
-                        acc[i][0] = fmaf(av, b0.x, acc[i][0]); acc[i][1] = fmaf(av, b0.y, acc[i][1]);
-                        acc[i][2] = fmaf(av, b0.z, acc[i][2]); acc[i][3] = fmaf(av, b0.w, acc[i][3]);
-                        acc[i][4] = fmaf(av, b1.x, acc[i][4]); acc[i][5] = fmaf(av, b1.y, acc[i][5]);
-                        acc[i][6] = fmaf(av, b1.z, acc[i][6]); acc[i][7] = fmaf(av, b1.w, acc[i][7]);
-                        acc[i][8] = fmaf(av, b2.x, acc[i][8]); acc[i][9] = fmaf(av, b2.y, acc[i][9]);
+                        ffma2(acc[i][0], acc[i][1], av, b0.x, b0.y);
+                        ffma2(acc[i][2], acc[i][3], av, b0.z, b0.w);
+                        ffma2(acc[i][4], acc[i][5], av, b1.x, b1.y);
+                        ffma2(acc[i][6], acc[i][7], av, b1.z, b1.w);
+                        ffma2(acc[i][8], acc[i][9], av, b2.x, b2.y);
                     }
                 }
             }
@@ -502,6 +512,106 @@ static int tail_launch(qmri_ctx* ctx, const HeadTailParams& p) {
     return QMRI_OK;
 }
 int tail_fp32(qmri_ctx* ctx, const HeadTailParams& p) { return ht_tile_h(p) == 4 ? tail_launch<4>(ctx, p) : tail_launch<8>(ctx, p); }
+
+
+// ---------------------------------------------------------------------------------------
+// Tensor-mode head / tail: the 10 (11) -> 64 and 64 -> 10 convs run through the 64 -> 64 tensor-core conv with zero-padded
+// weights; these two streaming kernels are what is left of them.
+//   head_pack:   planar fp32 [S][Cpl][H][W] (+ noise map), (v - min) / range folded in -> [S][H][W][64] hi / lo bf16, channels
+//                >= Cin zero.  A warp takes 32 consecutive pixels: coalesced plane reads (one pixel per lane), the values meet
+//                through shuffles, and every store instruction writes 512 contiguous bytes (lane = (pixel, 16-byte chunk)).
+//   tail_unpack: [S][H][W][64] hi / lo (channels 0 .. 9 hold the conv output) -> planar fp32 [S][10][H][W], v * range + min.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ht_pack2(float a, float b) {  // two floats -> bf16 pair (round to nearest even), a in the low half
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__global__ void __launch_bounds__(256) head_pack_kernel(HeadTailParams p) {
+    const int lane = threadIdx.x & 31;
+    const size_t HW = (size_t)p.H * p.W;
+    const size_t npx = (size_t)p.S * HW;
+    const size_t px0 = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;   // first pixel of this warp
+    if (px0 >= npx) return;
+    const int Cpl = p.noise_map ? p.Cin - 1 : p.Cin;
+    float v[11];
+    {
+        const size_t px = px0 + lane;
+        const bool ok = px < npx;
+        const size_t s = ok ? px / HW : 0, r = ok ? px - s * HW : 0;
+        float mn = 0.f, inv = 1.f;
+        if (p.minmax) {
+            mn = p.minmax[2 * s];
+            inv = 1.0f / (p.minmax[2 * s + 1] - mn);
+        }
+#pragma unroll
+        for (int c = 0; c < 11; ++c) {
+            float x = 0.f;
+            if (ok && c < Cpl) x = (__ldg(p.planar_in + (s * Cpl + c) * HW + r) - mn) * inv;
+            else if (ok && c == Cpl && p.noise_map) x = __ldg(p.noise_map + r);
+            v[c] = x;
+        }
+    }
+    const int j = lane & 7;   // 16-byte chunk = channels 8 j .. 8 j + 7
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int q = (lane >> 3) + 4 * k;   // pixel of the warp whose chunk j this lane stores
+        float w[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float a = __shfl_sync(0xffffffffu, v[c], q);
+            const float b = c < 3 ? __shfl_sync(0xffffffffu, v[8 + c], q) : 0.f;
+            w[c] = j == 0 ? a : (j == 1 ? b : 0.f);
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            hi[c] = ht_pack2(w[2 * c], w[2 * c + 1]);
+            const float h0 = __uint_as_float(hi[c] << 16), h1 = __uint_as_float(hi[c] & 0xffff0000u);
+            lo[c] = ht_pack2(w[2 * c] - h0, w[2 * c + 1] - h1);
+        }
+        const size_t px = px0 + q;
+        if (px < npx) {
+            *reinterpret_cast<uint4*>(p.nhwc_hi + px * 64 + 8 * j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(p.nhwc_lo + px * 64 + 8 * j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) tail_unpack_kernel(HeadTailParams p) {
+    const size_t HW = (size_t)p.H * p.W;
+    const size_t npx = (size_t)p.S * HW;
+    const size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npx) return;
+    const size_t s = px / HW, r = px - s * HW;
+    float mn = 0.f, rg = 1.f;
+    if (p.minmax) {
+        mn = p.minmax[2 * s];
+        rg = p.minmax[2 * s + 1] - mn;
+    }
+    const uint4 h0 = *reinterpret_cast<const uint4*>(p.nhwc_hi + px * 64), h1 = *reinterpret_cast<const uint4*>(p.nhwc_hi + px * 64 + 8);
+    const uint4 l0 = *reinterpret_cast<const uint4*>(p.nhwc_lo + px * 64), l1 = *reinterpret_cast<const uint4*>(p.nhwc_lo + px * 64 + 8);
+    const uint32_t hh[5] = {h0.x, h0.y, h0.z, h0.w, h1.x}, ll[5] = {l0.x, l0.y, l0.z, l0.w, l1.x};
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const float a = __uint_as_float(hh[c] << 16) + __uint_as_float(ll[c] << 16);
+        const float b = __uint_as_float(hh[c] & 0xffff0000u) + __uint_as_float(ll[c] & 0xffff0000u);
+        p.planar_out[(s * 10 + 2 * c) * HW + r] = a * rg + mn;
+        p.planar_out[(s * 10 + 2 * c + 1) * HW + r] = b * rg + mn;
+    }
+}
+int head_pack_tc(qmri_ctx* ctx, const HeadTailParams& p) {
+    if (p.Cin > 11 || !p.nhwc_hi || !p.nhwc_lo) return qmri_fail(QMRI_EINVAL, "head_pack_tc: Cin %d / missing planes", p.Cin);
+    const size_t npx = (size_t)p.S * p.H * p.W;
+    head_pack_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(p);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
+int tail_unpack_tc(qmri_ctx* ctx, const HeadTailParams& p) {
+    if (!p.nhwc_hi || !p.nhwc_lo) return qmri_fail(QMRI_EINVAL, "tail_unpack_tc: missing planes");
+    const size_t npx = (size_t)p.S * p.H * p.W;
+    tail_unpack_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(p);
+    QLAUNCH_CHECK(ctx);
+    return QMRI_OK;
+}
 
 int normalize_planar(qmri_ctx* ctx, const float* in, float* out, const float* minmax, size_t per_slice, int S, int undo) {
     dim3 grid((unsigned)((per_slice + 255) / 256), S);

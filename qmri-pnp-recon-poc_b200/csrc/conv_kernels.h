@@ -67,6 +67,8 @@ int conv3x3_fp32(qmri_ctx* ctx, const ConvParams& p);
 int resample_fp32(qmri_ctx* ctx, const ConvParams& p);
 int head_fp32(qmri_ctx* ctx, const HeadTailParams& p);
 int tail_fp32(qmri_ctx* ctx, const HeadTailParams& p);
+int head_pack_tc(qmri_ctx* ctx, const HeadTailParams& p);     // tensor-mode head: planar input -> 64-channel hi / lo planes (conv follows)
+int tail_unpack_tc(qmri_ctx* ctx, const HeadTailParams& p);   // tensor-mode tail: channels 0 .. 9 of the conv output -> planar fp32
 int tc_make_act_map(void* out_map, const void* base, int S, int H, int W, int C, int BW, int BH);
 int tc_make_down_map(void* out_map, const void* base, int S, int H, int W, int C, int dy, int dx, int BW, int BH);
 int tc_make_weight_map(void* out_map, const void* base, int K, int N, int BN);

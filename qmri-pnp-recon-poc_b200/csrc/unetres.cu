@@ -169,9 +169,21 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
         net->wmapp_h2[o].resize(64);
         net->wmapp_l2[o].resize(64);
         std::vector<uint16_t> hi, lo;
+        std::vector<float> wpad;
         for (int l = 0; l < 64 && net->tc_available; ++l) {
-            if (L[l].kind > 2) continue;
-            pack_layer_tc(L[l], weights[l], o, hi, lo);
+            LayerDesc dl = L[l];
+            const float* wsrc = weights[l];
+            if (dl.kind > 2) {
+                // head / tail in tensor mode: the same conv as a zero-padded 64 -> 64 layer ([co][ci][3][3], PyTorch order) - the
+                // 64 -> 64 tensor-core kernel is faster on 6 x the flops than the fp32 CUDA-core kernels were on the real ones
+                wpad.assign((size_t)64 * 64 * 9, 0.f);
+                for (int co = 0; co < dl.cout; ++co)
+                    for (int ci = 0; ci < dl.cin; ++ci)
+                        for (int t = 0; t < 9; ++t) wpad[((size_t)co * 64 + ci) * 9 + t] = weights[l][((size_t)co * dl.cin + ci) * 9 + t];
+                dl = LayerDesc{0, 64, 64};
+                wsrc = wpad.data();
+            }
+            pack_layer_tc(dl, wsrc, o, hi, lo);
             int r = dev_alloc(&net->wtc_hi[o][l], hi.size()) | dev_alloc(&net->wtc_lo[o][l], lo.size());
             if (r) {
                 unetres_free(net);
@@ -179,14 +191,14 @@ int unetres_create(qmri_ctx* ctx, int in_nc, const float* const* weights, int n_
             }
             cudaMemcpy(net->wtc_hi[o][l], hi.data(), hi.size() * 2, cudaMemcpyHostToDevice);
             cudaMemcpy(net->wtc_lo[o][l], lo.data(), lo.size() * 2, cudaMemcpyHostToDevice);
-            const int BN = tc_block_n(L[l].cout);
-            const int K = (L[l].kind == 0 ? 9 : L[l].kind == 1 ? 4 : 1) * L[l].cin;
-            const int N = (L[l].kind == 2 ? 4 : 1) * L[l].cout;
+            const int BN = tc_block_n(dl.cout);
+            const int K = (dl.kind == 0 ? 9 : dl.kind == 1 ? 4 : 1) * dl.cin;
+            const int N = (dl.kind == 2 ? 4 : 1) * dl.cout;
             r = tc_make_weight_map(&net->wmap_hi[o][l], net->wtc_hi[o][l], K, N, BN) |
                 tc_make_weight_map(&net->wmap_lo[o][l], net->wtc_lo[o][l], K, N, BN);
-            if (!r && L[l].kind == 0) {
+            if (!r && dl.kind == 0) {
                 int rows_main, rows_h2;
-                tc_pair_weight_boxes(L[l].cout, &rows_main, &rows_h2);
+                tc_pair_weight_boxes(dl.cout, &rows_main, &rows_h2);
                 r = tc_make_weight_map(&net->wmapp_hi[o][l], net->wtc_hi[o][l], K, N, rows_main) |
                     tc_make_weight_map(&net->wmapp_lo[o][l], net->wtc_lo[o][l], K, N, rows_main) |
                     tc_make_weight_map(&net->wmapp_h2[o][l], net->wtc_hi[o][l], K, N, rows_h2) |
@@ -428,8 +440,13 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
     hp.w = w[li++];
     hp.minmax = minmax;
     hp.S = S; hp.H = H; hp.W = W; hp.Cin = net->in_nc;
-    QCHECK(head_fp32(ctx, hp));
-    prof.mark(ctx, "head");
+    // QMRI_TC_HEADTAIL=0: the fp32 CUDA-core head / tail kernels of round 1 (A/B runs)
+    const char* ht_env = getenv("QMRI_TC_HEADTAIL");
+    const bool ht_tc = !(ht_env && atoi(ht_env) == 0);
+    if (!ht_tc) {
+        QCHECK(head_fp32(ctx, hp));
+        prof.mark(ctx, "head");
+    }
 
     auto tiles = [&](TcConvParams& p) {
         tc_tile_shape(p.W, p.H, &p.BW, &p.BH);
@@ -502,6 +519,13 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
         p.mapB_hi = &net->wmap_hi[orient][layer]; p.mapB_lo = &net->wmap_lo[orient][layer];
         return conv_tc(ctx, p);
     };
+    if (ht_tc) {  // head = pack to 64 channels (zeros above Cin) + the 64 -> 64 tensor conv with zero-padded weights
+        hp.nhwc_hi = hi[BT][0];
+        hp.nhwc_lo = lo[BT][0];
+        QCHECK(head_pack_tc(ctx, hp));
+        QCHECK(conv(0, BT, BX, 0, 0, -1, -1));
+        prof.mark(ctx, "head");
+    }
     for (int lvl = 0; lvl < 3; ++lvl) {
         for (int b = 0; b < 4; ++b) {
             int xin = (b == 0) ? BX : roleA[lvl];
@@ -538,7 +562,14 @@ static int forward_chunk_tc(qmri_net* net, const float* in, float* out, const fl
     tp.w = w[li++];
     tp.minmax = minmax;
     tp.S = S; tp.H = H; tp.W = W; tp.Cin = 64;
-    QCHECK(tail_fp32(ctx, tp));
+    if (ht_tc) {  // tail = the 64 -> 64 tensor conv (output channels >= 10 are zero weights) + unpack of channels 0 .. 9
+        QCHECK(conv(0, roleA[0], roleT[0], li - 1, 0, -1, -1));
+        tp.nhwc_hi = hi[roleT[0]][0];
+        tp.nhwc_lo = lo[roleT[0]][0];
+        QCHECK(tail_unpack_tc(ctx, tp));
+    } else {
+        QCHECK(tail_fp32(ctx, tp));
+    }
     prof.mark(ctx, "tail");
     prof.report(S);
     return QMRI_OK;
