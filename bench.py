@@ -521,7 +521,7 @@ def run_ours(args, rank, world, local_rank):
     max_chunk = int(os.environ.get("QMRI_NET_CHUNK", "128"))   # unetres.h max_chunk: slices per pass through the network
     chunks = -(-S // max_chunk)
     per_chunk = -(-S // chunks)
-    roofline = {"bound": "tensor", "kernel": f"UNetRes forward = 64 conv launches per pass of <= {max_chunk} slices (tc_conv3x3_pair_kernel: 58 3x3 convs = 97% of flops)",
+    roofline = {"bound": "tensor", "kernel": f"UNetRes forward = 66 launches per pass of <= {max_chunk} slices (tc_conv3x3_pair_kernel: 58 3x3 convs = 97% of the algorithmic flops, + head and tail as zero-padded 64 -> 64 convs)",
                 "achieved": fwd_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": fwd_tflops / tensor_peak,
                 "frac_of_3_product_ceiling": 3 * fwd_tflops / tensor_peak,
                 "frac_bound_from_step": fwd_flops * (iters - 1) / (step_ms * 1e-3) / 1e12 / tensor_peak,

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "qmri-pnp-recon-poc_b200", "lib", "libqmri_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
-MNEMONICS = ["UTCHMMA.2CTA", "UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCCP", "SYNCS", "UCGABAR", "FFMA", "HMMA", "LDS", "STS", "LDG", "STG", "LDL", "STL", "ATOMG", "RED", "SHFL"]
+MNEMONICS = ["UTCHMMA.2CTA", "UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UTCBAR", "UTCCP", "SYNCS", "UCGABAR", "R2UR", "ELECT", "FFMA2", "FFMA", "HMMA", "LDS", "STS", "LDG", "STG", "LDL", "STL", "ATOMG", "RED", "SHFL"]
 counts = collections.OrderedDict()
 arch = None
 cur = None
@@ -32,6 +32,8 @@ for line in sass.splitlines():
     op = m.group(1)
     counts[cur]["total"] += 1
     for mn in MNEMONICS:
+        if mn == "FFMA" and op.startswith("FFMA2"):
+            continue
         if op == mn or op.startswith(mn + "."):
             counts[cur][mn] += 1
             if mn == "UTCHMMA.2CTA":
