@@ -841,10 +841,9 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const int cidx = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const uint32_t slab_bytes = (uint32_t)((p.BH + 2) * p.BW * 128);
     const uint32_t dy_bytes = (uint32_t)(p.BW * 128);
-    // Dual-issuer mode (Cout = 64 layers).  One thread issues a tcgen05.mma every ~103 cycles at best, whatever its N
-    // (profiles/r02_tmem_a_bench.txt), so the two MMAs of a K step - N = 128 and N = 64, 96 cycles of tensor time - took ~206.  Warp 1
-    // keeps a_hi x [w_hi | w_lo]; warp 6 issues a_lo x w_hi into its OWN accumulator columns (MMAs of different threads are not ordered
-    // against each other, so they must not share an accumulator); the epilogue adds the third block.
+    // Dual-issuer mode (Cout = 64 layers) - RETIRED (launch_pair never sets it): a second warp issued a_lo x w_hi into its own accumulator
+    // columns to get around a ~103-cycle "issue floor" that was ptxas' register-to-uniform loop (see tc2_mma_elect); the lean epilogue of
+    // the 64 -> 64 instance no longer reads a third accumulator block.
     const bool dual = Cfg::DUAL_OK && (p.dual & 1);
     // Resident-weight mode (Cin = Cout = 64 layers).  With Cout = 64 a 128-pixel tile re-streamed the whole layer's weights (108 KB per
     // CTA: nine taps of [w_hi ; w_lo] and w_hi) next to 120 KB of activation slabs - 66 B/clk per SM at the tensor rate against the
@@ -1803,8 +1802,9 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
 // ------------------------------------------------------------------------------------------------
 // Operand-swapped 3x3 conv for the 64 -> 64 layers (Cin = Cout = 64).
 //
-// One thread issues a tcgen05.mma every ~103 cycles at best whatever its N (profiles/r02_tmem_a_bench.txt), so a layer whose GEMM
-// has only N = 64 output channels (128 with the hi / lo weight planes stacked) cannot feed the tensor pipe from the N side.  Here the
+// (Experiment, off by default, NOT brought forward to the warp-uniform issue loop / staging-tile epilogue of the pair kernel.)  Built when
+// MMA issue looked like a ~103-cycle hardware floor - it was ptxas' register-to-uniform loop around UTCHMMAs issued from divergent code,
+// see tc2_mma_elect - under which a layer with only N = 64 output channels could not feed the tensor pipe from the N side.  Here the
 // roles are swapped: the stacked weights [w_hi ; w_lo] are the M = 128 A operand and live in TENSOR MEMORY for the whole kernel
 // (576 bf16 per row = 288 columns, written once per CTA with tcgen05.st), the PIXELS are the N dimension - 224 of them per tile (14
 // rows x 16), the widest N the remaining 224 TMEM columns allow for the accumulator - and only the activation slabs stream through

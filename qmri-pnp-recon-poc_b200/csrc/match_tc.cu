@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) match_tc_kernel(const __grid_
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shuffle: warp-uniform for ptxas
     const int total_work = p.ptiles * p.nsplit;
 
-    // Two MMA-issuing warps for complex pixels: one thread gets a tcgen05.mma out every ~103 cycles at best (profiles/r02_tmem_a_bench.txt),
+    // Two MMA-issuing warps for complex pixels (built against a ~103-cycle "issue floor" that turned out to be ptxas' register-to-uniform
+    // loop around every UTCHMMA issued from divergent code - tc_ptx.cuh; with the warp-uniform loop one issuer does as well, two are kept):
     // and the real and the imaginary accumulator are independent - warp 1 issues the real part's MMAs, the last warp the imaginary
     // part's.  Both commit on the stage / accumulator / pixel-tile barriers (count 2).  QMRI_K2_ISSUERS=1 keeps a single issuer.
     const bool two = CPLX && p.issuers == 2;
