@@ -1721,9 +1721,11 @@ static int launch_pair(qmri_ctx* ctx, const TcConvParams& p, TcK k) {
         if (!dbg_this) k.dual = 0;
     }
     k.resw = (Cfg::DUAL_OK && !resw_off && p.Cin == TC_BK) ? (resw_stages >= 2 ? resw_stages : 1) : 0;
-    static const bool tma_out_off = getenv("QMRI_TC_TMAOUT") && !strcmp(getenv("QMRI_TC_TMAOUT"), "0");  // A/B switch
+    const char* tmaout_s = getenv("QMRI_TC_TMAOUT");   // A/B switches, read per call: tests toggle them
+    const bool tma_out_off = tmaout_s && !strcmp(tmaout_s, "0");
     // tma_out: 2 = two staging buffers + two slab stages, 1 = one staging buffer + three slab stages (QMRI_TC_OUTBUF=1 / 2 forces one)
-    static const int outbuf_env = getenv("QMRI_TC_OUTBUF") ? atoi(getenv("QMRI_TC_OUTBUF")) : 0;
+    const char* outbuf_s = getenv("QMRI_TC_OUTBUF");
+    const int outbuf_env = outbuf_s ? atoi(outbuf_s) : 0;
     k.tma_out = (k.resw && p.mapO_hi && p.mapO_lo && !tma_out_off) ? (outbuf_env == 1 || outbuf_env == 2 ? outbuf_env : (p.res1_hi ? 2 : 1)) : 0;
     k.res_tma = (k.tma_out && p.res1_hi && p.mapR_hi && p.mapR_lo) ? 1 : 0;
     static const int l2pf_env = getenv("QMRI_TC_L2PF") ? atoi(getenv("QMRI_TC_L2PF")) : 0;   // A/B switch: 1 = on for all pair layers

@@ -320,6 +320,29 @@ def test_denoiser_operand_swapped_64_channel_kernel(q, monkeypatch):
     assert rel_l2(y_swap[..., 1], unetres.denoise_matlab_layout(sd, A[..., 1])) <= TOL_DENOISER
 
 
+def test_denoiser_ab_switches_of_the_64_channel_path(q, monkeypatch):
+    """The 64 -> 64 layers' data path (staging tile + bulk tensor stores / loads, one or two staging buffers) against its fallbacks:
+    QMRI_TC_TMAOUT=0 (16-byte global accesses), QMRI_TC_OUTBUF=1 / 2 (forced buffer count) - the arithmetic and its order are the same,
+    so the outputs are bit-identical - and QMRI_TC_HEADTAIL=0 (fp32 CUDA-core head / tail instead of pack + tensor conv + unpack)."""
+    from oracle import unetres
+    sd = unetres.make_state_dict(10, seed=0)
+    rng = np.random.default_rng(8)
+    A = rng.random((224, 224, 10, 2))
+    net = q.UNetRes(sd, in_nc=10)
+    net.set_precision("tc")
+    y0 = net.denoise(A)
+    for key, val in [("QMRI_TC_TMAOUT", "0"), ("QMRI_TC_OUTBUF", "1"), ("QMRI_TC_OUTBUF", "2")]:
+        monkeypatch.setenv(key, val)
+        y = net.denoise(A)
+        monkeypatch.delenv(key)
+        assert np.array_equal(y, y0), (key, val, rel_l2(y, y0))
+    monkeypatch.setenv("QMRI_TC_HEADTAIL", "0")
+    y_fp32_ht = net.denoise(A)
+    monkeypatch.delenv("QMRI_TC_HEADTAIL")
+    assert rel_l2(y_fp32_ht, y0) <= 1e-5
+    assert rel_l2(y0[..., 1], unetres.denoise_matlab_layout(sd, A[..., 1])) <= TOL_DENOISER
+
+
 def test_denoiser_multi_level_11_channels(q):
     import torch
     from oracle import unetres
