@@ -5,6 +5,7 @@ descriptors into uniform registers - ~100 cycles per MMA, the "issue floor" of r
 that pattern comes back next to an MMA of the conv / matching kernels.  Allowed: the 12 MMAs of the retired second-issuer block of the
 64 -> 64 instance (never executed) and the opt-in operand-swapped experiment kernel."""
 import collections
+import functools
 import os
 import re
 import shutil
@@ -17,6 +18,7 @@ from conftest import ROOT
 LIB = os.path.join(ROOT, "qmri-pnp-recon-poc_b200", "lib", "libqmri_b200.so")
 
 
+@functools.lru_cache(maxsize=1)
 def _sass_by_kernel():
     out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
     cur, lines = None, collections.defaultdict(list)
